@@ -1,0 +1,392 @@
+// Host launchers for catalogue scoring (+ the exact-fp32 FFMA variant for small catalogues).
+//   lrb_score_topk   precision 0 -> score_topk_tc_kernel (tcgen05/TMEM/TMA, bf16 operands)
+//                    precision 1 -> score_topk_f32_kernel (fp32 FFMA, bit-comparable with the
+//                                   fp32 reference `x @ E^T + bias`, model/lru.py:85)
+//   lrb_score_dense  API-compatible dense logits for LRURec.forward
+#include "api_util.h"
+#include "score_topk_tc.cuh"
+
+#include <cuda.h>
+#include <climits>
+#include <cmath>
+
+namespace lrb {
+
+// ============================================================================================
+// fp32 path.  Thread = user row (state in registers), CTA = 128 rows, item chunks of 64 rows
+// staged in shared memory and read with broadcast LDS.128.
+// ============================================================================================
+namespace f32 {
+
+constexpr int ROWS = 128;   // users per CTA
+constexpr int IT = 64;      // items per shared-memory chunk
+constexpr int D = 64;
+
+struct Params {
+  const float* u;        // [B][64]
+  const float* table;    // [rows][64]
+  const float* bias_pad; // [ceil(rows/256)*256]
+  int B;
+  int rows;
+  int row_offset;
+  int K;
+  const int* excl_sorted;
+  const uint32_t* excl_bloom;
+  int excl_stride;
+  float* part_scores;
+  int* part_ids;
+  int* part_cnt;
+  int slots;             // == number of item splits == gridDim.y
+  float* dense_out;
+  long long dense_ld;
+};
+
+template <bool kDense>
+__global__ void __launch_bounds__(ROWS) score_f32_kernel(const Params p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* sE = reinterpret_cast<float*>(smem);                  // [IT][64]
+  float* sBias = sE + IT * D;                                   // [IT]
+  float* sOut = sBias + IT;                                     // dense: [ROWS][IT+1]
+  float* sListS = sBias + IT;                                   // topk:  [K][ROWS]
+  int* sListI = reinterpret_cast<int*>(sListS + (kDense ? 0 : p.K * ROWS));
+  __shared__ int sCnt[2 * ROWS];   // [0..ROWS) entries held, [ROWS..2*ROWS) index of the worst entry
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x * ROWS + tid;
+  const bool live = b < p.B;
+
+  float u[D];
+#pragma unroll
+  for (int k = 0; k < D; k += 4) {
+    float4 v = live ? *reinterpret_cast<const float4*>(p.u + static_cast<size_t>(b) * D + k)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    u[k] = v.x; u[k + 1] = v.y; u[k + 2] = v.z; u[k + 3] = v.w;
+  }
+
+  // item range of this split, aligned to chunks
+  const int chunks = (p.rows + IT - 1) / IT;
+  const int c0 = static_cast<int>((static_cast<long long>(blockIdx.y) * chunks) / gridDim.y);
+  const int c1 = static_cast<int>((static_cast<long long>(blockIdx.y + 1) * chunks) / gridDim.y);
+
+  float own_thr = -INFINITY;
+  const int* excl = nullptr;
+  uint32_t bloom0 = 0u, bloom1 = 0u, bloom2 = 0u, bloom3 = 0u;
+  if (!kDense) {
+    sCnt[tid] = 0;
+    if (live && p.excl_sorted != nullptr) {
+      excl = p.excl_sorted + static_cast<size_t>(b) * p.excl_stride;
+      const uint4 bw = *reinterpret_cast<const uint4*>(p.excl_bloom + static_cast<size_t>(b) * 4);
+      bloom0 = bw.x; bloom1 = bw.y; bloom2 = bw.z; bloom3 = bw.w;
+    }
+  }
+  const uint32_t ls_a = smem_u32(sListS + tid);
+  const uint32_t li_a = smem_u32(sListI + tid);
+  const uint32_t ln_a = smem_u32(&sCnt[tid]);
+  const int limit_gid = p.row_offset + p.rows;
+
+  for (int c = c0; c < c1; ++c) {
+    const int i0 = c * IT;
+    __syncthreads();
+    // stage IT x 64 floats (zero beyond rows) and the bias
+    for (int e = tid; e < IT * D / 4; e += ROWS) {
+      const int it = e / (D / 4);
+      const int k4 = e - it * (D / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 + it < p.rows)
+        v = *reinterpret_cast<const float4*>(p.table + static_cast<size_t>(i0 + it) * D + k4 * 4);
+      reinterpret_cast<float4*>(sE)[e] = v;
+    }
+    if (tid < IT) sBias[tid] = p.bias_pad[i0 + tid];
+    __syncthreads();
+
+    for (int it = 0; it < IT; ++it) {
+      const float4* e4 = reinterpret_cast<const float4*>(sE + it * D);
+      // strict left-to-right fp32 accumulation in 4 interleaved partial sums keeps the result
+      // within ~1e-7 relative of any other fp32 summation order.
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < D / 4; ++k4) {
+        const float4 ev = e4[k4];
+        a0 = fmaf(u[4 * k4 + 0], ev.x, a0);
+        a1 = fmaf(u[4 * k4 + 1], ev.y, a1);
+        a2 = fmaf(u[4 * k4 + 2], ev.z, a2);
+        a3 = fmaf(u[4 * k4 + 3], ev.w, a3);
+      }
+      const float s = ((a0 + a1) + (a2 + a3)) + sBias[it];
+      if (kDense) {
+        sOut[tid * (IT + 1) + it] = s;
+      } else if (live && s >= own_thr) {
+        const int gid = p.row_offset + i0 + it;
+        const int bw = (gid >> 5) & 3;
+        const uint32_t bword = bw == 0 ? bloom0 : (bw == 1 ? bloom1 : (bw == 2 ? bloom2 : bloom3));
+        own_thr = tc::topk_consider<ROWS>(s, gid, limit_gid, own_thr, ls_a, li_a, ln_a, p.K, excl,
+                                          p.excl_stride, bword);
+      }
+    }
+    if (kDense) {
+      __syncthreads();
+      // coalesced write-out: 64 consecutive floats per row
+      for (int e = tid; e < ROWS * IT; e += ROWS) {
+        const int rr = e / IT;
+        const int it = e - rr * IT;
+        const int row = blockIdx.x * ROWS + rr;
+        if (row < p.B && i0 + it < p.rows)
+          p.dense_out[static_cast<size_t>(row) * p.dense_ld + i0 + it] = sOut[rr * (IT + 1) + it];
+      }
+    }
+  }
+
+  if (!kDense && live) {
+    const int cnt = sCnt[tid];
+    const size_t base = static_cast<size_t>(b) * p.slots + blockIdx.y;
+    p.part_cnt[base] = cnt;
+    for (int i = 0; i < cnt; ++i) {
+      p.part_scores[base * p.K + i] = sListS[i * ROWS + tid];
+      p.part_ids[base * p.K + i] = sListI[i * ROWS + tid];
+    }
+  }
+}
+
+inline int splits_for(int B, long long rows, int sms) {
+  const int m_tiles = (B + ROWS - 1) / ROWS;
+  const long long chunks = (rows + IT - 1) / IT;
+  long long want = (2LL * sms + m_tiles - 1) / m_tiles;
+  long long max_splits = (chunks + 3) / 4;   // at least 4 chunks (256 items) per split
+  if (max_splits < 1) max_splits = 1;
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  return static_cast<int>(want);
+}
+
+}  // namespace f32
+
+// ============================================================================================
+// tcgen05 path: decomposition + tensor maps + launch
+// ============================================================================================
+namespace {
+
+struct Decomp {
+  int m_tiles, n_tiles, s_full, rem, full_tiles, y_tiles, grid, slots;
+};
+
+Decomp decompose(int B, long long rows, int sms) {
+  Decomp d;
+  d.m_tiles = (B + tc::BM - 1) / tc::BM;
+  d.n_tiles = static_cast<int>((rows + tc::BN - 1) / tc::BN);
+  long long work = static_cast<long long>(d.m_tiles) * d.n_tiles;
+  int G = static_cast<int>(work < sms ? work : sms);
+  if (G < 1) G = 1;
+  d.s_full = G / d.m_tiles;
+  d.rem = G - d.s_full * d.m_tiles;
+  if (d.s_full == 0) {
+    d.rem = G;
+    d.y_tiles = d.n_tiles;
+    d.full_tiles = 0;
+  } else if (d.rem == 0) {
+    d.y_tiles = 0;
+    d.full_tiles = d.n_tiles;
+  } else {
+    // per-CTA work: full stream = full_tiles / s_full ; shared stream = m_tiles * y / rem
+    double y = static_cast<double>(d.n_tiles) /
+               (static_cast<double>(d.s_full) * d.m_tiles / d.rem + 1.0);
+    d.y_tiles = static_cast<int>(std::floor(y + 0.5));
+    if (d.y_tiles > d.n_tiles) d.y_tiles = d.n_tiles;
+    if (d.y_tiles <= 0) { d.y_tiles = 0; d.rem = 0; }
+    d.full_tiles = d.n_tiles - d.y_tiles;
+  }
+  d.grid = d.s_full * d.m_tiles + d.rem;
+  d.slots = 2 * (d.s_full + (d.rem > 0 ? 2 : 0));
+  return d;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    tried = true;
+  }
+  return fn;
+}
+
+// [rows][64] bf16 row-major, box = 64 x box_rows, 128-byte swizzle, OOB rows read as zero.
+int make_tmap_bf16_k64(CUtensorMap* out, const void* ptr, unsigned long long rows, unsigned box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(LRB_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {64ull, rows};
+  cuuint64_t strides[1] = {128ull};
+  cuuint32_t box[2] = {64u, box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(LRB_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return LRB_OK;
+}
+
+template <int KMAX, int NS, bool kDense>
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const tc::ScoreParams& p, int grid,
+              cudaStream_t st) {
+  using L = tc::SmemLayout<KMAX, NS>;
+  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense>;
+  LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
+  kern<<<grid, tc::THREADS, L::kAlloc, st>>>(ta, tb, p);
+  LRB_CUDA_TRY(cudaGetLastError());
+  return LRB_OK;
+}
+
+}  // namespace
+}  // namespace lrb
+
+#ifdef LRB_DEBUG_MODES
+static int g_debug_mode = 0;
+extern "C" void lrb_debug_set_score_mode(int m) { g_debug_mode = m; }
+#else
+static const int g_debug_mode = 0;
+#endif
+
+extern "C" {
+
+int lrb_score_topk_slots(int B, int64_t rows, int precision, int* slots) {
+  LRB_REQUIRE(B > 0 && rows > 0 && slots != nullptr, "lrb_score_topk_slots: bad arguments");
+  int sms = lrb::device_sm_count();
+  if (sms <= 0) sms = 148;
+  if (precision == 0) {
+    *slots = lrb::decompose(B, rows, sms).slots;
+  } else if (precision == 1) {
+    *slots = lrb::f32::splits_for(B, rows, sms);
+  } else {
+    return lrb::set_error(LRB_ERR_BAD_ARG, "precision must be 0 (bf16) or 1 (fp32)");
+  }
+  return LRB_OK;
+}
+
+static size_t gthr_bytes(int B) {
+  const size_t m_tiles = (static_cast<size_t>(B) + lrb::tc::BM - 1) / lrb::tc::BM;
+  return (m_tiles * lrb::tc::BM * sizeof(int) + 255) & ~static_cast<size_t>(255);
+}
+
+size_t lrb_score_scratch_bytes(int B) {
+  int sms = lrb::device_sm_count();
+  if (sms <= 0) sms = 148;
+  const size_t ring = static_cast<size_t>(sms) * lrb::tc::EPI_THREADS * lrb::tc::RING_GROUPS *
+                      lrb::tc::RING_REC_BYTES;
+  return gthr_bytes(B) + ring;
+}
+
+int lrb_score_topk(const void* u, const void* table, const float* bias_pad, const void* bias_blk,
+                   int B, int64_t rows,
+                   int64_t row_offset, const int32_t* excl_sorted, const uint32_t* excl_bloom,
+                   int excl_stride, int K, int precision, float* part_scores, int32_t* part_ids,
+                   int32_t* part_cnt, int slots, void* scratch, void* stream) {
+  using namespace lrb;
+  int rc = check_arch();
+  if (rc != LRB_OK) return rc;
+  LRB_REQUIRE(u && table && part_scores && part_ids && part_cnt, "lrb_score_topk: null pointer");
+  LRB_REQUIRE(precision != 1 || bias_pad != nullptr, "lrb_score_topk: the fp32 path needs bias_pad");
+  LRB_REQUIRE(B > 0 && rows > 0 && rows + row_offset < INT_MAX, "lrb_score_topk: bad B/rows");
+  LRB_REQUIRE(K >= 1 && K <= LRB_MAX_K, "lrb_score_topk: K must be in [1, %d]", LRB_MAX_K);
+  LRB_REQUIRE((excl_sorted == nullptr) == (excl_bloom == nullptr), "lrb_score_topk: exclusion list and bloom filter must come together");
+  cudaStream_t st = as_stream(stream);
+  int sms = device_sm_count();
+  if (precision == 1) {
+    const int splits = f32::splits_for(B, rows, sms);
+    LRB_REQUIRE(slots == splits, "lrb_score_topk: slots=%d but lrb_score_topk_slots says %d", slots, splits);
+    f32::Params p;
+    p.u = static_cast<const float*>(u);
+    p.table = static_cast<const float*>(table);
+    p.bias_pad = bias_pad;
+    p.B = B; p.rows = static_cast<int>(rows); p.row_offset = static_cast<int>(row_offset); p.K = K;
+    p.excl_sorted = excl_sorted; p.excl_bloom = excl_bloom; p.excl_stride = excl_stride;
+    p.part_scores = part_scores; p.part_ids = part_ids; p.part_cnt = part_cnt; p.slots = slots;
+    p.dense_out = nullptr; p.dense_ld = 0;
+    const size_t smem = (f32::IT * f32::D + f32::IT) * 4 + static_cast<size_t>(K) * f32::ROWS * 8;
+    auto kern = f32::score_f32_kernel<false>;
+    LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid((B + f32::ROWS - 1) / f32::ROWS, splits);
+    kern<<<grid, f32::ROWS, smem, st>>>(p);
+    LRB_CUDA_TRY(cudaGetLastError());
+    return LRB_OK;
+  }
+  LRB_REQUIRE(precision == 0, "precision must be 0 (bf16) or 1 (fp32)");
+  LRB_REQUIRE(scratch != nullptr, "lrb_score_topk: scratch is required for the bf16 path");
+  const Decomp d = decompose(B, rows, sms);
+  LRB_REQUIRE(slots == d.slots, "lrb_score_topk: slots=%d but lrb_score_topk_slots says %d", slots, d.slots);
+  CUtensorMap ta, tb;
+  rc = make_tmap_bf16_k64(&ta, u, static_cast<unsigned long long>(B), tc::BM);
+  if (rc != LRB_OK) return rc;
+  rc = make_tmap_bf16_k64(&tb, table, static_cast<unsigned long long>(rows), tc::BN);
+  if (rc != LRB_OK) return rc;
+  tc::ScoreParams p;
+  p.B = B; p.m_tiles = d.m_tiles; p.rows = static_cast<int>(rows); p.n_tiles = d.n_tiles;
+  p.row_offset = static_cast<int>(row_offset); p.K = K;
+  p.bias_blk = static_cast<const uint8_t*>(bias_blk);
+  p.excl_sorted = excl_sorted; p.excl_bloom = excl_bloom; p.excl_stride = excl_stride;
+  p.gthr = static_cast<int*>(scratch);
+  p.ring = static_cast<uint8_t*>(scratch) + gthr_bytes(B);
+  p.part_scores = part_scores; p.part_ids = part_ids; p.part_cnt = part_cnt; p.slots = d.slots;
+  p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode;
+  p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
+  LRB_CUDA_TRY(cudaMemsetAsync(part_cnt, 0, static_cast<size_t>(B) * d.slots * sizeof(int), st));
+  LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, gthr_bytes(B), st));
+  if (K <= 20) return launch_tc<20, 3, false>(ta, tb, p, d.grid, st);
+  if (K <= 32) return launch_tc<32, 3, false>(ta, tb, p, d.grid, st);
+  return launch_tc<50, 2, false>(ta, tb, p, d.grid, st);
+}
+
+int lrb_score_dense(const void* x, const void* table, const float* bias_pad, const void* bias_blk,
+                    int64_t M, int64_t rows, int precision, float* out, int64_t ld_out, void* stream) {
+  using namespace lrb;
+  int rc = check_arch();
+  if (rc != LRB_OK) return rc;
+  LRB_REQUIRE(x && table && out, "lrb_score_dense: null pointer");
+  LRB_REQUIRE(precision != 1 || bias_pad != nullptr, "lrb_score_dense: the fp32 path needs bias_pad");
+  LRB_REQUIRE(M > 0 && M < INT_MAX && rows > 0 && rows < INT_MAX && ld_out >= rows, "lrb_score_dense: bad shape");
+  cudaStream_t st = as_stream(stream);
+  int sms = device_sm_count();
+  if (precision == 1) {
+    f32::Params p;
+    p.u = static_cast<const float*>(x);
+    p.table = static_cast<const float*>(table);
+    p.bias_pad = bias_pad;
+    p.B = static_cast<int>(M); p.rows = static_cast<int>(rows); p.row_offset = 0; p.K = 0;
+    p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
+    p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
+    p.dense_out = out; p.dense_ld = ld_out;
+    const int splits = f32::splits_for(static_cast<int>(M), rows, sms);
+    const size_t smem = (f32::IT * f32::D + f32::IT) * 4 + static_cast<size_t>(f32::ROWS) * (f32::IT + 1) * 4;
+    auto kern = f32::score_f32_kernel<true>;
+    LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid(static_cast<unsigned>((M + f32::ROWS - 1) / f32::ROWS), splits);
+    kern<<<grid, f32::ROWS, smem, st>>>(p);
+    LRB_CUDA_TRY(cudaGetLastError());
+    return LRB_OK;
+  }
+  LRB_REQUIRE(precision == 0, "precision must be 0 (bf16) or 1 (fp32)");
+  const Decomp d = decompose(static_cast<int>(M), rows, sms);
+  CUtensorMap ta, tb;
+  rc = make_tmap_bf16_k64(&ta, x, static_cast<unsigned long long>(M), tc::BM);
+  if (rc != LRB_OK) return rc;
+  rc = make_tmap_bf16_k64(&tb, table, static_cast<unsigned long long>(rows), tc::BN);
+  if (rc != LRB_OK) return rc;
+  tc::ScoreParams p;
+  p.B = static_cast<int>(M); p.m_tiles = d.m_tiles; p.rows = static_cast<int>(rows); p.n_tiles = d.n_tiles;
+  p.row_offset = 0; p.K = 1; p.bias_blk = static_cast<const uint8_t*>(bias_blk);
+  p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
+  p.gthr = nullptr; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
+  p.dense_out = out; p.dense_ld = ld_out; p.debug_mode = 0;
+  p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
+  return launch_tc<20, 3, true>(ta, tb, p, d.grid, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,640 @@
+// Full-catalogue scoring fused with a streaming per-user top-K  (north_star subsystem 2).
+//
+// Replaces, for the last position only, the reference chain
+//     scores = x @ E^T + bias                      model/lru.py:85
+//     scores[b, history] = -1e9 ; scores[:,0]=-1e9 trainer/lru.py:36-38
+//     torch.topk(scores, k)                        trainer/lru.py:82-84
+// with one persistent sm_100a kernel:
+//     TMA (SWIZZLE_128B)  ->  tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM)
+//     ->  tcgen05.ld epilogue: group max (FMNMX3), threshold filter, rare slow path = dump the
+//         16-score group to a ring; rings are drained warp-wide (lock-step) into per-thread top-K sets.
+// The B x N score matrix never leaves the SM.
+//
+// Tile: 128 users (TMEM lanes) x 256 items (TMEM columns) x K=64; two TMEM accumulator stages.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warp 3 = builds the "ones" block, warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4)..,
+// column half (w-4)/4).  The bias is folded into the GEMM as a fifth K=16 MMA per tile.
+#pragma once
+
+#include <cuda.h>
+#include "common.cuh"
+
+namespace lrb {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 128 + EPI_THREADS;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+
+struct ScoreParams {
+  int B;             // real users (rows >= B of the padded user matrix are ignored)
+  int m_tiles;       // padded users / 128
+  int rows;          // real local item rows
+  int n_tiles;       // ceil(rows / 256)
+  int row_offset;    // global item id of local row 0
+  int K;             // list length (<= KMAX)
+  const uint8_t* bias_blk;     // folded bias: [n_tiles] tiles of BIASBLK_BYTES (canonical no-swizzle
+                               // K-major [256][16] bf16: col 0..2 = hi/mid/lo split of bias, -inf
+                               // in col 0 beyond `rows`); nullptr = bias is identically zero
+  const int* excl_sorted;      // [B][excl_stride] ascending global ids, INT_MAX padded; null = none
+  const uint32_t* excl_bloom;  // [B][4] 128-bit membership filter over (id & 127)
+  int excl_stride;
+  int* gthr;                   // [m_tiles*128] ordered-int shared lower bounds (memset 0x80)
+  uint8_t* ring;               // [gridDim.x][EPI_THREADS][RING_GROUPS][RING_REC_BYTES] candidate rings
+  float* part_scores;          // [B][slots][K]
+  int* part_ids;               // [B][slots][K]
+  int* part_cnt;               // [B][slots]   (zeroed by the host wrapper)
+  int slots;
+  float* dense_out;            // dense mode only: [B][dense_ld], columns < rows written
+  long long dense_ld;
+  int debug_mode;              // harness only (LRB_DEBUG_MODES): 2 = null epilogue, 3 = TMEM loads only
+  // stream decomposition (host computed, see score_decompose())
+  int s_full;        // number of full streams (each = m_tiles CTAs, one per user tile)
+  int rem;           // CTAs in the shared stream
+  int full_tiles;    // item tiles covered by the full streams  [0, full_tiles)
+  int y_tiles;       // item tiles covered by the shared stream [full_tiles, n_tiles)
+};
+
+struct Segment {
+  int m;      // user tile
+  int n0;     // first item tile
+  int n1;     // one past the last item tile
+  int slot;   // partial-list slot (before the x2 for the column half)
+};
+
+// Deterministic walk over the segments owned by one CTA; every warp role runs the same walk.
+struct SegmentWalk {
+  int full;              // 1 = CTA belongs to a full stream
+  int m, n0, n1, slot;   // the single segment of a full-stream CTA
+  long long w, w_end;    // flattened (m * y + j) range of a shared-stream CTA
+  int y, nbase, s_full;
+  bool done;
+
+  __device__ SegmentWalk(const ScoreParams& p, int cta) {
+    s_full = p.s_full;
+    y = p.y_tiles;
+    nbase = p.full_tiles;
+    done = false;
+    if (cta < p.s_full * p.m_tiles) {
+      full = 1;
+      int s = cta / p.m_tiles;
+      m = cta - s * p.m_tiles;
+      n0 = static_cast<int>((static_cast<long long>(s) * p.full_tiles) / p.s_full);
+      n1 = static_cast<int>((static_cast<long long>(s + 1) * p.full_tiles) / p.s_full);
+      slot = s;
+      w = w_end = 0;
+    } else {
+      full = 0;
+      int j = cta - p.s_full * p.m_tiles;
+      long long total = static_cast<long long>(p.m_tiles) * p.y_tiles;
+      w = (total * j) / p.rem;
+      w_end = (total * (j + 1)) / p.rem;
+      m = n0 = n1 = slot = 0;
+    }
+  }
+  __device__ bool next(Segment& s) {
+    if (done) return false;
+    if (full) {
+      done = true;
+      if (n1 <= n0) return false;
+      s.m = m; s.n0 = n0; s.n1 = n1; s.slot = slot;
+      return true;
+    }
+    if (w >= w_end) { done = true; return false; }
+    int mm = static_cast<int>(w / y);
+    int j0 = static_cast<int>(w - static_cast<long long>(mm) * y);
+    long long len = y - j0;
+    if (len > w_end - w) len = w_end - w;
+    s.m = mm;
+    s.n0 = nbase + j0;
+    s.n1 = nbase + j0 + static_cast<int>(len);
+    s.slot = s_full + (j0 != 0 ? 1 : 0);
+    w += len;
+    return true;
+  }
+};
+
+// -------------------------------------------------------------------------------------------
+// Slow path: one score that passed the threshold filter.  Checks bounds and the exclusion list,
+// then offers it to this thread's candidate set: an UNSORTED array of K (score,id) pairs in shared
+// memory (entry i at base + i*STRIDE*4) with the position of the worst entry cached, so that an
+// accepted candidate costs one overwrite plus one rescan of K independent loads (no dependent
+// shift chain).  ln[0] = entries held, ln[STRIDE] = index of the worst entry.
+// Returns the thread's own K-th best score (-inf while the set is not full).
+// All pointers are 32-bit shared-space addresses.
+// -------------------------------------------------------------------------------------------
+template <int STRIDE>
+LRB_DEVINL float topk_consider_inl(float s, int gid, int row_limit_gid, float own_thr,
+                                   uint32_t ls, uint32_t li, uint32_t ln, int K,
+                                   const int* excl, uint32_t excl_s, int excl_stride,
+                                   uint32_t bloom_word) {
+  if (gid >= row_limit_gid) return own_thr;   // padded item column
+  if (!(s == s)) return own_thr;              // NaN never ranks
+  if (excl != nullptr && ((bloom_word >> (gid & 31)) & 1u)) {
+    int lo = 0, hi = excl_stride;
+    if (excl_s != 0u) {   // shared-memory copy of this row's sorted exclusion list
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lds_s32(excl_s + mid * 4) < gid) lo = mid + 1; else hi = mid;
+      }
+      if (lo < excl_stride && lds_s32(excl_s + lo * 4) == gid) return own_thr;
+    } else {
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(excl + mid) < gid) lo = mid + 1; else hi = mid;
+      }
+      if (lo < excl_stride && __ldg(excl + lo) == gid) return own_thr;  // in the user's history
+    }
+  }
+  constexpr uint32_t ES = STRIDE * 4;  // byte stride between consecutive entries
+  const int n = lds_s32(ln);
+  if (n < K) {
+    sts_f32(ls + n * ES, s);
+    sts_s32(li + n * ES, gid);
+    sts_s32(ln, n + 1);
+    if (n + 1 < K) return -INFINITY;
+  } else {
+    const int wp = lds_s32(ln + ES);
+    const float ws = lds_f32(ls + wp * ES);
+    const int wi = lds_s32(li + wp * ES);
+    if (!better(s, gid, ws, wi)) return own_thr;
+    sts_f32(ls + wp * ES, s);
+    sts_s32(li + wp * ES, gid);
+  }
+  // rescan: worst = lowest score, ties broken towards the higher id
+  float m = lds_f32(ls);
+  int mi = lds_s32(li);
+  int mp = 0;
+#pragma unroll 4
+  for (int i = 1; i < K; ++i) {
+    const float v = lds_f32(ls + i * ES);
+    if (v <= m) {
+      const int vi = lds_s32(li + i * ES);
+      if (v < m || vi > mi) { m = v; mi = vi; mp = i; }
+    }
+  }
+  sts_s32(ln + ES, mp);
+  return m;
+}
+
+template <int STRIDE>
+__device__ __noinline__ float topk_consider(float s, int gid, int row_limit_gid, float own_thr,
+                                            uint32_t ls, uint32_t li, uint32_t ln, int K,
+                                            const int* excl, int excl_stride, uint32_t bloom_word) {
+  return topk_consider_inl<STRIDE>(s, gid, row_limit_gid, own_thr, ls, li, ln, K, excl, 0u, excl_stride,
+                                   bloom_word);
+}
+
+// -------------------------------------------------------------------------------------------
+// Deferred candidates.  When the maximum of a 16-score group reaches the thread's threshold the
+// thread does NOT look at the individual scores: it dumps the group (16 floats + the global id of
+// its first column) into a private ring in global memory (L2 resident, RING_GROUPS records of
+// RING_REC_BYTES) and moves on -- 5 stores on a path that typically has a single active lane.
+// The ring is drained by compact_ring(), which the whole warp enters together (lock-step): every
+// lane repeatedly picks the best remaining score of its current record with a branch-free argmax
+// and all lanes insert at the same time, so the insert cost is paid once per warp, not per lane.
+// -------------------------------------------------------------------------------------------
+constexpr int RING_GROUPS = 16;
+constexpr int RING_REC_BYTES = 80;   // 16 fp32 + int32 gid0, padded to a multiple of 16 B
+
+struct RingRec {
+  float4 a, b, c, d;
+  int gid0;
+};
+LRB_DEVINL RingRec load_rec(const float4* ring, int g, bool act) {
+  RingRec r;
+  if (act) {
+    const float4* rec = ring + g * (RING_REC_BYTES / 16);
+    r.a = rec[0]; r.b = rec[1]; r.c = rec[2]; r.d = rec[3];
+    r.gid0 = reinterpret_cast<const int*>(rec + 4)[0];
+  } else {
+    const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    r.a = ninf; r.b = ninf; r.c = ninf; r.d = ninf;
+    r.gid0 = 0;
+  }
+  return r;
+}
+
+template <int STRIDE>
+__device__ __noinline__ float compact_ring(const float4* ring, int cnt, float own_thr,
+                                           int row_limit_gid, uint32_t ls, uint32_t li, uint32_t ln,
+                                           int K, const int* excl, uint32_t excl_s, int excl_stride,
+                                           uint32_t bloom0, uint32_t bloom1, uint32_t bloom2,
+                                           uint32_t bloom3) {
+  const int max_cnt = __reduce_max_sync(0xffffffffu, cnt);
+  RingRec nxt = load_rec(ring, 0, 0 < cnt);
+  for (int g = 0; g < max_cnt; ++g) {
+    const bool act = g < cnt;
+    const RingRec cur = nxt;
+    nxt = load_rec(ring, g + 1, g + 1 < cnt);   // prefetch while this record is processed
+    float s[16];
+    const int gid0 = cur.gid0;
+    s[0] = cur.a.x; s[1] = cur.a.y; s[2] = cur.a.z; s[3] = cur.a.w;
+    s[4] = cur.b.x; s[5] = cur.b.y; s[6] = cur.b.z; s[7] = cur.b.w;
+    s[8] = cur.c.x; s[9] = cur.c.y; s[10] = cur.c.z; s[11] = cur.c.w;
+    s[12] = cur.d.x; s[13] = cur.d.y; s[14] = cur.d.z; s[15] = cur.d.w;
+    while (true) {
+      float best = -INFINITY;
+      int bj = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool gt = s[j] > best;   // strict: the lowest column wins ties (lower id first)
+        best = gt ? s[j] : best;
+        bj = gt ? j : bj;
+      }
+      const bool pass = act && best > -INFINITY && best >= own_thr;
+      if (!__any_sync(0xffffffffu, pass)) break;
+      if (pass) {
+        const int gid = gid0 + bj;
+        const int bw = (gid >> 5) & 3;
+        const uint32_t bword = bw == 0 ? bloom0 : (bw == 1 ? bloom1 : (bw == 2 ? bloom2 : bloom3));
+        own_thr = topk_consider_inl<STRIDE>(best, gid, row_limit_gid, own_thr, ls, li, ln, K, excl,
+                                            excl_s, excl_stride, bword);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s[j] = (pass && j == bj) ? -INFINITY : s[j];
+    }
+  }
+  return own_thr;
+}
+
+constexpr int EX_CAP = 56;   // ints per row of the shared-memory exclusion copy (L <= 54)
+constexpr int BIASBLK_BYTES = BN * 16 * 2;   // one tile of the folded-bias K=16 block (8 KB)
+constexpr int ONES_BYTES = BM * 16 * 2;      // the matching [128][16] "ones" A block (4 KB)
+
+template <int KMAX, int NS>
+struct SmemLayout {
+  static constexpr bool kExclSmem = (KMAX <= 20);   // larger K variants have no room for it
+  static constexpr int kStage = B_BYTES + BIASBLK_BYTES;   // item tile + its bias block
+  static constexpr int kA = 0;
+  static constexpr int kOnes = kA + A_BYTES;
+  static constexpr int kB = kOnes + ONES_BYTES;            // 20 KB offset: 1024-aligned
+  static constexpr int kListS = kB + NS * kStage;
+  static constexpr int kListI = kListS + KMAX * EPI_THREADS * 4;
+  static constexpr int kListN = kListI + KMAX * EPI_THREADS * 4;
+  static constexpr int kRowThr = kListN + EPI_THREADS * 8;
+  static constexpr int kExcl = kRowThr + BM * 4;
+  static constexpr int kBars = kExcl + (kExclSmem ? BM * EX_CAP * 4 : 0);
+  // barriers: full[NS], empty[NS], tmem_full[2], tmem_empty[2], a_full, a_empty
+  static constexpr int kNumBars = 2 * NS + 2 * ACC_STAGES + 2;
+  static constexpr int kTmemPtr = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kAlloc = kTotal + 1024;  // slack for manual 1024-B alignment
+  static_assert(kAlloc <= 232448, "shared memory budget exceeded");
+  static_assert(kB % 1024 == 0 && kStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-B alignment");
+};
+
+// No-swizzle K-major canonical layout of a [rows][16] bf16 block (UMMA "INTERLEAVE"): 8x8 core
+// matrices of 128 contiguous bytes; the two core matrices of one 8-row group (K halves) are LBO =
+// 128 B apart, consecutive 8-row groups SBO = 256 B apart.
+LRB_DEVINL uint64_t umma_desc_k16_nosw(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 16;   // LBO
+  d |= static_cast<uint64_t>(256 >> 4) << 32;   // SBO
+  d |= static_cast<uint64_t>(1) << 46;          // version
+  return d;                                     // layout type 0 = no swizzle
+}
+
+template <int KMAX, int NS, bool kDense>
+__global__ void __launch_bounds__(THREADS, 1)
+score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                     const __grid_constant__ CUtensorMap tmap_b, const ScoreParams p) {
+  using L = SmemLayout<KMAX, NS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  uint8_t* sA = smem + L::kA;
+  uint8_t* sOnes = smem + L::kOnes;
+  uint8_t* sB = smem + L::kB;
+  float* sListS = reinterpret_cast<float*>(smem + L::kListS);
+  int* sListI = reinterpret_cast<int*>(smem + L::kListI);
+  int* sListN = reinterpret_cast<int*>(smem + L::kListN);
+  int* sRowThr = reinterpret_cast<int*>(smem + L::kRowThr);
+  int* sExcl = reinterpret_cast<int*>(smem + L::kExcl);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + NS;
+  uint64_t* tmem_full_bar = bars + 2 * NS;
+  uint64_t* tmem_empty_bar = bars + 2 * NS + ACC_STAGES;
+  uint64_t* a_full_bar = bars + 2 * NS + 2 * ACC_STAGES;
+  uint64_t* a_empty_bar = a_full_bar + 1;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool has_bias = p.bias_blk != nullptr;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS);
+    }
+    mbar_init(a_full_bar, 1);
+    mbar_init(a_empty_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_s, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp == 3) {
+    // "ones" block: column 0..2 = 1.0 (they multiply the hi/mid/lo bf16 terms of the bias)
+    for (int i = lane; i < ONES_BYTES / 2; i += 32) {
+      // canonical no-swizzle layout: element (row, k) at (row/8)*256 + (k/8)*128 + (row%8)*16 + (k%8)*2
+      const int grp = i >> 7;          // 128 elements per 8-row group (2 core matrices)
+      const int rem = i & 127;
+      const int khalf = rem >> 6;
+      const int k = khalf * 8 + (rem & 7);
+      (void)grp;
+      reinterpret_cast<__nv_bfloat16*>(sOnes)[i] = __float2bfloat16(k < 3 ? 1.0f : 0.0f);
+    }
+    // make the generic-proxy writes visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      SegmentWalk walk(p, blockIdx.x);
+      Segment sg;
+      int stage = 0;
+      uint32_t phase = 0;
+      int seg_idx = 0;
+      const uint32_t stage_tx = B_BYTES + (has_bias ? BIASBLK_BYTES : 0);
+      while (walk.next(sg)) {
+        if (seg_idx > 0) mbar_wait(a_empty_bar, (seg_idx - 1) & 1);
+        mbar_expect_tx(a_full_bar, A_BYTES);
+        tma_load_2d(sA, &tmap_a, a_full_bar, 0, sg.m * BM);
+        for (int n = sg.n0; n < sg.n1; ++n) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          uint8_t* st = sB + stage * L::kStage;
+          tma_load_2d(st, &tmap_b, &full_bar[stage], 0, n * BN);
+          if (has_bias)
+            bulk_load_1d(st + B_BYTES, p.bias_blk + static_cast<size_t>(n) * BIASBLK_BYTES,
+                         BIASBLK_BYTES, &full_bar[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        ++seg_idx;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      SegmentWalk walk(p, blockIdx.x);
+      Segment sg;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      int seg_idx = 0;
+      const uint64_t desc_a0 = umma_desc_k_sw128(smem_u32(sA));
+      const uint64_t desc_ones = umma_desc_k16_nosw(smem_u32(sOnes));
+      while (walk.next(sg)) {
+        mbar_wait(a_full_bar, seg_idx & 1);
+        for (int n = sg.n0; n < sg.n1; ++n) {
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(sB + stage * L::kStage);
+          const uint64_t desc_b0 = umma_desc_k_sw128(st);
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * BN);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the 128-B swizzle atom: +2 in 16-B units
+            umma_bf16_ss(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+          }
+          // folded bias: D += ones[128x16] * bias_blk[256x16]^T  (hi + mid + lo bf16 terms)
+          if (has_bias) umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_nosw(st + B_BYTES), idesc, 1u);
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full_bar[acc]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+        umma_commit(a_empty_bar);
+        ++seg_idx;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;          // 0..7
+    const int quad = ew & 3;          // TMEM lane quadrant == warp % 4
+    const int half = ew >> 2;         // column half of the tile
+    const int et = ew * 32 + lane;    // epilogue thread index 0..255
+    const int r = quad * 32 + lane;   // row inside the user tile
+    const uint32_t ls = smem_u32(sListS + et);
+    const uint32_t li = smem_u32(sListI + et);
+    const uint32_t ln = smem_u32(sListN + et);
+
+    SegmentWalk walk(p, blockIdx.x);
+    Segment sg;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    while (walk.next(sg)) {
+      const int b = sg.m * BM + r;
+      const bool live = b < p.B;
+      // per-segment state reset
+      sts_s32(ln, 0);
+      float own_thr = -INFINITY;
+      int published = INT_MIN;
+      if (half == 0) sRowThr[r] = INT_MIN;
+      const int* excl = nullptr;
+      uint32_t bloom0 = 0u, bloom1 = 0u, bloom2 = 0u, bloom3 = 0u;
+      if (!kDense && live && p.excl_sorted != nullptr) {
+        excl = p.excl_sorted + static_cast<size_t>(b) * p.excl_stride;
+        const uint4 bw = *reinterpret_cast<const uint4*>(p.excl_bloom + static_cast<size_t>(b) * 4);
+        bloom0 = bw.x; bloom1 = bw.y; bloom2 = bw.z; bloom3 = bw.w;
+      }
+      uint32_t excl_s = 0u;
+      if (!kDense && L::kExclSmem && p.excl_sorted != nullptr && p.excl_stride <= EX_CAP) {
+        // stage the 128 rows' sorted exclusion lists in shared memory (binary-searched in the
+        // lock-step compaction, where a global-memory search would stall the whole warp)
+        const int total = BM * p.excl_stride;
+        for (int i = et; i < total; i += EPI_THREADS) {
+          const int rr = i / p.excl_stride;
+          const int cc = i - rr * p.excl_stride;
+          const int bb = sg.m * BM + rr;
+          sExcl[rr * EX_CAP + cc] =
+              bb < p.B ? p.excl_sorted[static_cast<size_t>(bb) * p.excl_stride + cc] : INT_MAX;
+        }
+        excl_s = smem_u32(sExcl + r * EX_CAP);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // sRowThr reset / sExcl visible
+      int cnt = 0;   // records waiting in this thread's ring
+      int k_glb = INT_MIN;   // shared lower bound, fetched one tile ahead of its use
+      float4* ring = reinterpret_cast<float4*>(
+          p.ring + (static_cast<size_t>(blockIdx.x) * EPI_THREADS + et) * (RING_GROUPS * RING_REC_BYTES));
+      const int limit_gid = p.row_offset + p.rows;
+
+      for (int n = sg.n0; n < sg.n1; ++n) {
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+
+        // rows beyond B never produce candidates: their threshold is +inf
+        float t_eff = live ? own_thr : INFINITY;
+        if (!kDense && live) {
+          const int k_row = sRowThr[r];
+          const int kk = k_row > k_glb ? k_row : k_glb;
+          if (kk != INT_MIN) t_eff = fmaxf(own_thr, key_to_float(kk));
+          // issue the load for the NEXT tile now; its latency hides behind this tile's work
+          k_glb = *reinterpret_cast<volatile int*>(p.gthr + b);
+        }
+
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN + half * (BN / 2));
+        const int col_gid0 = p.row_offset + n * BN + half * (BN / 2);
+
+#ifdef LRB_DEBUG_MODES
+        if (p.debug_mode == 2 || p.debug_mode == 3) {
+          if (p.debug_mode == 3) {
+            uint32_t w[32];
+            uint32_t acc_x = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld_32x32(taddr + c * 32, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc_x ^= w[j];
+            }
+            if (acc_x == 0x12345678u) p.gthr[0] = 1;   // keep the loads alive
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+#endif
+        uint32_t v[2][32];
+        tmem_ld_32x32(taddr, v[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < 3) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+          float s[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[c & 1][j]);
+          if (kDense) {
+            const int row = sg.m * BM + r;
+            const int col0 = n * BN + half * (BN / 2) + c * 32;
+            if (row < p.B) {
+              float* dst = p.dense_out + static_cast<size_t>(row) * p.dense_ld + col0;
+              if (col0 + 32 <= p.rows && (p.dense_ld & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  reinterpret_cast<float4*>(dst)[j] =
+                      make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.rows) dst[j] = s[j];
+              }
+            }
+          } else {
+            float gmax[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const float* q = s + g * 16;
+              const float m1 = max3(q[0], q[1], q[2]);
+              const float m2 = max3(q[3], q[4], q[5]);
+              const float m3 = max3(q[6], q[7], q[8]);
+              const float m4 = max3(q[9], q[10], q[11]);
+              const float m5 = max3(q[12], q[13], q[14]);
+              const float m6 = max3(m1, m2, m3);
+              const float m7 = max3(m4, m5, q[15]);
+              gmax[g] = fmaxf(m6, m7);
+            }
+            // one branch per 32 columns on the hot path; the group split happens inside it
+            if (fmaxf(gmax[0], gmax[1]) >= t_eff) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                if (gmax[g] >= t_eff) {
+                  const float* q = s + g * 16;
+                  float4* rec = ring + cnt * (RING_REC_BYTES / 16);
+                  rec[0] = make_float4(q[0], q[1], q[2], q[3]);
+                  rec[1] = make_float4(q[4], q[5], q[6], q[7]);
+                  rec[2] = make_float4(q[8], q[9], q[10], q[11]);
+                  rec[3] = make_float4(q[12], q[13], q[14], q[15]);
+                  reinterpret_cast<int*>(rec + 4)[0] = col_gid0 + c * 32 + g * 16;
+                  ++cnt;
+                }
+              }
+            }
+          }
+          if (c < 3) tmem_ld_wait();
+          if (c == 2) {
+            // all four TMEM loads of this accumulator stage have landed in registers:
+            // hand the stage back to the MMA warp before chewing on the last chunk.
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+        }
+        if (!kDense) {
+          // uniform point, once per tile: a tile adds at most 8 records per thread, so draining
+          // whenever some lane holds more than RING_GROUPS-8 keeps every ring within capacity.
+          if (__any_sync(0xffffffffu, cnt > RING_GROUPS - 8)) {
+            own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, limit_gid, ls, li, ln, p.K, excl,
+                                                excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
+            cnt = 0;
+            const int key = float_to_key(own_thr);
+            if (live && own_thr > -INFINITY && key > published) {
+              published = key;
+              atomicMax(&sRowThr[r], key);
+              atomicMax(p.gthr + b, key);
+            }
+          }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+
+      if (!kDense) {
+        // final drain of this segment (whole warp, lock-step)
+        own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, limit_gid, ls, li, ln, p.K, excl,
+                                            excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
+        cnt = 0;
+      }
+
+      if (!kDense && live) {
+        const int held = lds_s32(ln);
+        const size_t base = (static_cast<size_t>(b) * p.slots + (sg.slot * 2 + half));
+        p.part_cnt[base] = held;
+        for (int i = 0; i < held; ++i) {
+          p.part_scores[base * p.K + i] = lds_f32(ls + i * EPI_THREADS * 4);
+          p.part_ids[base * p.K + i] = lds_s32(li + i * EPI_THREADS * 4);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // before the next segment resets sRowThr
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace lrb
