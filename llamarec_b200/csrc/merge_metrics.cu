@@ -1,0 +1,197 @@
+// k-way merge of per-split / per-rank candidate sets + Recall/MRR/NDCG + candidate emission,
+// one fused kernel (north_star subsystem 3).
+//
+// Replaces, per user,
+//   rank = (-scores).argsort(dim=1)            trainer/utils.py:56   (full sort of N+1 scores)
+//   hits / Recall / MRR / NDCG @ ks            trainer/utils.py:61-88
+//   torch.topk(scores, 20) + `label in top20`  trainer/lru.py:82-88, 124-132
+// by a selection over the <= n_lists*K_in candidates the scoring kernel kept: the label's rank in
+// the merged list is its rank in the full catalogue whenever that rank is < K_out, which is all
+// the metrics at k <= K_out need.
+//
+// One warp per user.  Entries live in registers (up to 16 per lane) or, for very wide fan-in
+// (tiny batches split over many CTAs), are re-read from global memory each round.
+#include "api_util.h"
+#include "common.cuh"
+
+#include <climits>
+
+namespace lrb {
+namespace mm {
+
+constexpr int WARPS = 8;
+constexpr int PER_LANE = 16;   // register-resident entries per lane (512 per user)
+constexpr int MAX_KS = 8;
+
+struct Params {
+  const float* list_scores;
+  const int* list_ids;
+  const int* list_cnt;         // may be null
+  int n_lists;
+  long long stride_list, stride_user, cnt_stride_list, cnt_stride_user;
+  int K_in, B, K_out;
+  const long long* labels;     // may be null
+  int ks[MAX_KS];
+  int n_ks;
+  float* top_scores;           // [B][K_out]
+  int* top_ids;                // [B][K_out]
+  int* label_rank;             // [B] (may be null)
+  float* metric_sums;          // [3*n_ks] (may be null)
+};
+
+struct Best {
+  float s;
+  int id;
+  int lane;
+};
+
+LRB_DEVINL Best warp_best(float s, int id, int lane) {
+  Best b{s, id, lane};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, b.s, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, b.id, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, b.lane, o);
+    if (better(os, oi, b.s, b.id) || (os == b.s && oi == b.id && ol < b.lane)) {
+      b.s = os; b.id = oi; b.lane = ol;
+    }
+  }
+  return b;
+}
+
+__global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params p) {
+  __shared__ float s_sums[WARPS][3 * MAX_KS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WARPS + warp;
+  float acc[3 * MAX_KS];
+#pragma unroll
+  for (int i = 0; i < 3 * MAX_KS; ++i) acc[i] = 0.f;
+
+  if (b < p.B) {
+    const float* sc = p.list_scores + static_cast<size_t>(b) * p.stride_user;
+    const int* id = p.list_ids + static_cast<size_t>(b) * p.stride_user;
+    const int total_slots = p.n_lists * p.K_in;
+    const bool in_regs = total_slots <= 32 * PER_LANE;
+
+    float es[PER_LANE];
+    int ei[PER_LANE];
+    if (in_regs) {
+#pragma unroll
+      for (int q = 0; q < PER_LANE; ++q) {
+        const int e = q * 32 + lane;
+        es[q] = -INFINITY;
+        ei[q] = INT_MAX;
+        if (e < total_slots) {
+          const int l = e / p.K_in;
+          const int i = e - l * p.K_in;
+          const int cnt = p.list_cnt ? p.list_cnt[b * p.cnt_stride_user + l * p.cnt_stride_list] : p.K_in;
+          if (i < cnt) {
+            es[q] = sc[l * p.stride_list + i];
+            ei[q] = id[l * p.stride_list + i];
+          }
+        }
+      }
+    }
+
+    int my_rank = -1;
+    const long long label = p.labels ? p.labels[b] : -1;
+    // floor for the global-memory path: entries must be strictly "after" the previous winner
+    float prev_s = INFINITY;
+    int prev_id = -1;
+    for (int k = 0; k < p.K_out; ++k) {
+      float bs = -INFINITY;
+      int bi = INT_MAX;
+      int bq = -1;
+      if (in_regs) {
+#pragma unroll
+        for (int q = 0; q < PER_LANE; ++q) {
+          if (better(es[q], ei[q], bs, bi)) { bs = es[q]; bi = ei[q]; bq = q; }
+        }
+      } else {
+        for (int e = lane; e < total_slots; e += 32) {
+          const int l = e / p.K_in;
+          const int i = e - l * p.K_in;
+          const int cnt = p.list_cnt ? p.list_cnt[b * p.cnt_stride_user + l * p.cnt_stride_list] : p.K_in;
+          if (i >= cnt) continue;
+          const float s = sc[l * p.stride_list + i];
+          const int d = id[l * p.stride_list + i];
+          // skip everything already emitted: strictly after (prev_s, prev_id) in the total order
+          if (!(better(prev_s, prev_id, s, d))) continue;
+          if (better(s, d, bs, bi)) { bs = s; bi = d; }
+        }
+      }
+      const Best w = warp_best(bs, bi, lane);
+      if (in_regs && w.lane == lane && bq >= 0) {
+#pragma unroll
+        for (int q = 0; q < PER_LANE; ++q)
+          if (q == bq) { es[q] = -INFINITY; ei[q] = INT_MAX; }
+      }
+      prev_s = w.s;
+      prev_id = w.id;
+      const bool valid = w.id != INT_MAX;
+      if (lane == 0) {
+        p.top_scores[static_cast<size_t>(b) * p.K_out + k] = valid ? w.s : -INFINITY;
+        p.top_ids[static_cast<size_t>(b) * p.K_out + k] = valid ? w.id : -1;
+      }
+      if (valid && my_rank < 0 && static_cast<long long>(w.id) == label) my_rank = k;
+    }
+    if (p.label_rank && lane == 0) p.label_rank[b] = my_rank;
+    if (p.labels && my_rank >= 0 && lane == 0) {
+      // one relevant item per user: Recall@k = [r<k], MRR@k = [r<k]/(r+1), NDCG@k = [r<k]/log2(r+2)
+      // (trainer/utils.py:61-88 with answer_count == 1, hence idcg == 1)
+      const float mrr = 1.0f / static_cast<float>(my_rank + 1);
+      const float ndcg = 1.0f / log2f(static_cast<float>(my_rank + 2));
+#pragma unroll
+      for (int i = 0; i < MAX_KS; ++i) {
+        if (i < p.n_ks && my_rank < p.ks[i]) {
+          acc[3 * i + 0] = 1.0f;
+          acc[3 * i + 1] = mrr;
+          acc[3 * i + 2] = ndcg;
+        }
+      }
+    }
+  }
+  if (p.metric_sums != nullptr) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 3 * MAX_KS; ++i) s_sums[warp][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * p.n_ks) {
+      float t = 0.f;
+      for (int w = 0; w < WARPS; ++w) t += s_sums[w][threadIdx.x];
+      if (t != 0.f) atomicAdd(p.metric_sums + threadIdx.x, t);
+    }
+  }
+}
+
+}  // namespace mm
+}  // namespace lrb
+
+extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_ids, const int32_t* list_cnt,
+                                 int n_lists, int64_t stride_list, int64_t stride_user,
+                                 int64_t cnt_stride_list, int64_t cnt_stride_user, int K_in, int B, int K_out,
+                                 const int64_t* labels, const int32_t* ks_host, int n_ks, float* top_scores,
+                                 int32_t* top_ids, int32_t* label_rank, float* metric_sums, void* stream) {
+  using namespace lrb;
+  int rc = check_arch();
+  if (rc != LRB_OK) return rc;
+  LRB_REQUIRE(list_scores && list_ids && top_scores && top_ids, "lrb_merge_metrics: null pointer");
+  LRB_REQUIRE(n_lists >= 1 && K_in >= 1 && B >= 1 && K_out >= 1, "lrb_merge_metrics: bad shape");
+  LRB_REQUIRE(n_ks >= 0 && n_ks <= mm::MAX_KS, "lrb_merge_metrics: at most %d cut-offs", mm::MAX_KS);
+  LRB_REQUIRE(n_ks == 0 || ks_host != nullptr, "lrb_merge_metrics: ks missing");
+  mm::Params p;
+  p.list_scores = list_scores; p.list_ids = list_ids; p.list_cnt = list_cnt; p.n_lists = n_lists;
+  p.stride_list = stride_list; p.stride_user = stride_user;
+  p.cnt_stride_list = cnt_stride_list; p.cnt_stride_user = cnt_stride_user;
+  p.K_in = K_in; p.B = B; p.K_out = K_out;
+  p.labels = reinterpret_cast<const long long*>(labels);
+  for (int i = 0; i < mm::MAX_KS; ++i) p.ks[i] = i < n_ks ? ks_host[i] : 0;
+  p.n_ks = labels ? n_ks : 0;
+  p.top_scores = top_scores; p.top_ids = top_ids; p.label_rank = label_rank;
+  p.metric_sums = (labels && n_ks > 0) ? metric_sums : nullptr;
+  const int grid = (B + mm::WARPS - 1) / mm::WARPS;
+  mm::merge_metrics_kernel<<<grid, mm::WARPS * 32, 0, as_stream(stream)>>>(p);
+  LRB_CUDA_TRY(cudaGetLastError());
+  return LRB_OK;
+}

@@ -250,9 +250,12 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const tc::ScoreParam
 
 #ifdef LRB_DEBUG_MODES
 static int g_debug_mode = 0;
+static long long* g_debug_stats = nullptr;
 extern "C" void lrb_debug_set_score_mode(int m) { g_debug_mode = m; }
+extern "C" void lrb_debug_set_stats(long long* p) { g_debug_stats = p; }
 #else
 static const int g_debug_mode = 0;
+static long long* const g_debug_stats = nullptr;
 #endif
 
 extern "C" {
@@ -335,7 +338,7 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
   p.gthr = static_cast<int*>(scratch);
   p.ring = static_cast<uint8_t*>(scratch) + gthr_bytes(B);
   p.part_scores = part_scores; p.part_ids = part_ids; p.part_cnt = part_cnt; p.slots = d.slots;
-  p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode;
+  p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
   LRB_CUDA_TRY(cudaMemsetAsync(part_cnt, 0, static_cast<size_t>(B) * d.slots * sizeof(int), st));
   LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, gthr_bytes(B), st));
@@ -384,7 +387,7 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
   p.row_offset = 0; p.K = 1; p.bias_blk = static_cast<const uint8_t*>(bias_blk);
   p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
   p.gthr = nullptr; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
-  p.dense_out = out; p.dense_ld = ld_out; p.debug_mode = 0;
+  p.dense_out = out; p.dense_ld = ld_out; p.debug_mode = 0; p.debug_stats = nullptr;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
   return launch_tc<20, 3, true>(ta, tb, p, d.grid, st);
 }

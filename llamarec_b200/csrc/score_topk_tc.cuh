@@ -55,6 +55,7 @@ struct ScoreParams {
   float* dense_out;            // dense mode only: [B][dense_ld], columns < rows written
   long long dense_ld;
   int debug_mode;              // harness only (LRB_DEBUG_MODES): 2 = null epilogue, 3 = TMEM loads only
+  long long* debug_stats;      // harness only: per CTA {cycles, appended records, compactions, tiles}
   // stream decomposition (host computed, see score_decompose())
   int s_full;        // number of full streams (each = m_tiles CTAs, one per user tile)
   int rem;           // CTAs in the shared stream
@@ -332,6 +333,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool has_bias = p.bias_blk != nullptr;
+#ifdef LRB_DEBUG_MODES
+  const long long dbg_t0 = clock64();
+  long long dbg_appends = 0, dbg_compactions = 0, dbg_tiles = 0, dbg_wait = 0, dbg_compact = 0, dbg_first = 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -487,8 +492,15 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int limit_gid = p.row_offset + p.rows;
 
       for (int n = sg.n0; n < sg.n1; ++n) {
+#ifdef LRB_DEBUG_MODES
+        const long long w0 = clock64();
+#endif
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
+#ifdef LRB_DEBUG_MODES
+        dbg_wait += clock64() - w0;
+        if (n == sg.n0 + 64) dbg_first = clock64() - dbg_t0;
+#endif
 
         // rows beyond B never produce candidates: their threshold is +inf
         float t_eff = live ? own_thr : INFINITY;
@@ -594,8 +606,16 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // uniform point, once per tile: a tile adds at most 8 records per thread, so draining
           // whenever some lane holds more than RING_GROUPS-8 keeps every ring within capacity.
           if (__any_sync(0xffffffffu, cnt > RING_GROUPS - 8)) {
+#ifdef LRB_DEBUG_MODES
+            dbg_appends += cnt;
+            if (lane == 0) dbg_compactions += 1;
+            const long long c0 = clock64();
+#endif
             own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, limit_gid, ls, li, ln, p.K, excl,
                                                 excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
+#ifdef LRB_DEBUG_MODES
+            dbg_compact += clock64() - c0;
+#endif
             cnt = 0;
             const int key = float_to_key(own_thr);
             if (live && own_thr > -INFINITY && key > published) {
@@ -608,6 +628,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
 
+#ifdef LRB_DEBUG_MODES
+      dbg_appends += cnt;
+      if (lane == 0 && quad == 0 && half == 0) dbg_tiles += sg.n1 - sg.n0;
+#endif
       if (!kDense) {
         // final drain of this segment (whole warp, lock-step)
         own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, limit_gid, ls, li, ln, p.K, excl,
@@ -628,12 +652,30 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   }
 
+#ifdef LRB_DEBUG_MODES
+  if (p.debug_stats != nullptr) {
+    if (dbg_appends) atomicAdd(reinterpret_cast<unsigned long long*>(p.debug_stats + blockIdx.x * 4 + 1),
+                               static_cast<unsigned long long>(dbg_appends));
+    if (dbg_compactions) atomicAdd(reinterpret_cast<unsigned long long*>(p.debug_stats + blockIdx.x * 4 + 2),
+                                   static_cast<unsigned long long>(dbg_compactions));
+    if (dbg_tiles) atomicAdd(reinterpret_cast<unsigned long long*>(p.debug_stats + blockIdx.x * 4 + 3),
+                             static_cast<unsigned long long>(dbg_tiles));
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+#ifdef LRB_DEBUG_MODES
+  if (p.debug_stats != nullptr && threadIdx.x == 0) p.debug_stats[blockIdx.x * 4] = clock64() - dbg_t0;
+  if (p.debug_stats != nullptr && threadIdx.x == 128) {   // epilogue warp 0, lane 0
+    p.debug_stats[148 * 4 + blockIdx.x * 4 + 0] = dbg_wait;
+    p.debug_stats[148 * 4 + blockIdx.x * 4 + 1] = dbg_compact;
+    p.debug_stats[148 * 4 + blockIdx.x * 4 + 2] = dbg_first;
+  }
+#endif
 }
 
 }  // namespace tc

@@ -1,0 +1,135 @@
+"""Verbalizer with the reference's interface (trainer/verb.py:420-643, copy in demo/verb.py).
+
+`ManualVerbalizer(tokenizer, classes, label_words, prefix, multi_token_handler, post_log_softmax)` keeps
+the constructor and `process_logits(logits[B, V]) -> [B, C]`.  The fast path is
+
+    score_hidden(hidden_last[B, H], lm_head_weight[V, H]) -> [B, C]
+
+which never forms the [B, V] logits: the CUDA kernel multiplies only the label-word rows of the
+lm_head (model/llm.py:113-114 projects all T positions onto all V tokens) and applies
+project -> (softmax -> log) -> aggregate in the same launch.
+"""
+from __future__ import annotations
+
+from typing import List, Mapping, Optional, Sequence, Union
+
+import torch
+
+from . import _lib
+
+
+class ManualVerbalizer:
+    def __init__(self, tokenizer, classes: Optional[Sequence] = None, num_classes: Optional[int] = None,
+                 label_words: Optional[Union[Sequence, Mapping]] = None, prefix: Optional[str] = " ",
+                 multi_token_handler: Optional[str] = "first", post_log_softmax: Optional[bool] = True):
+        self.tokenizer = tokenizer
+        if classes is not None and num_classes is not None:
+            assert len(classes) == num_classes, "len(classes) != num_classes"
+        self.classes = list(classes) if classes is not None else None
+        self.num_classes = len(self.classes) if self.classes is not None else num_classes
+        self.prefix = prefix
+        self.multi_token_handler = multi_token_handler
+        self.post_log_softmax = post_log_softmax
+        self._label_words = None
+        if label_words is not None:
+            self.label_words = label_words
+
+    # ---- label words (trainer/verb.py:136-160 setter semantics, :463-522) -------------------------
+    @property
+    def label_words(self):
+        return self._label_words
+
+    @label_words.setter
+    def label_words(self, label_words):
+        if label_words is None:
+            return
+        if isinstance(label_words, Mapping):
+            if self.classes is None:
+                self.classes = list(label_words.keys())
+                self.num_classes = len(self.classes)
+            label_words = [label_words[c] for c in self.classes]
+        label_words = list(label_words)
+        if len(label_words) > 0 and isinstance(label_words[0], str):
+            label_words = [[w] for w in label_words]
+        with_prefix: List[List[str]] = []
+        for words in label_words:
+            row = []
+            for w in words:
+                row.append(w.split("<!>")[1] if w.startswith("<!>") else (self.prefix or "") + w)
+            with_prefix.append(row)
+        self._label_words = with_prefix
+        self.generate_parameters()
+
+    def generate_parameters(self) -> None:
+        ids = [[self.tokenizer.encode(w, add_special_tokens=False) for w in words] for words in self._label_words]
+        max_len = max(max(len(t) for t in per) for per in ids)
+        max_words = max(len(per) for per in ids)
+        C = len(ids)
+        words_ids = torch.zeros(C, max_words, max_len, dtype=torch.int64)
+        words_ids_mask = torch.zeros(C, max_words, max_len, dtype=torch.int64)
+        for c, per in enumerate(ids):
+            for w, toks in enumerate(per):
+                words_ids[c, w, : len(toks)] = torch.tensor(toks, dtype=torch.int64)
+                words_ids_mask[c, w, : len(toks)] = 1
+        self.label_words_ids = words_ids                                   # [C, W, T]
+        self.words_ids_mask = words_ids_mask                               # [C, W, T]
+        self.label_words_mask = torch.clamp(words_ids_mask.sum(dim=-1), max=1)   # [C, W]
+        self._dev_cache = {}
+
+    # ---- fused fast path ---------------------------------------------------------------------------
+    def _device_params(self, dev):
+        key = str(dev)
+        if key not in self._dev_cache:
+            first = self.label_words_ids[:, :, 0].to(torch.int32).contiguous().to(dev)
+            mask = self.label_words_mask.to(torch.uint8).contiguous().to(dev)
+            self._dev_cache[key] = (first, mask)
+        return self._dev_cache[key]
+
+    @torch.no_grad()
+    def score_hidden(self, hidden_last: torch.Tensor, lm_head_weight: torch.Tensor,
+                     round_logits_to_bf16: bool = True) -> torch.Tensor:
+        """[B, H] bf16 x label rows of [V, H] bf16 -> [B, C] fp32 label scores.
+
+        round_logits_to_bf16 mirrors `lm_head(hidden).float()` of a bf16 model (model/llm.py:113-114),
+        whose logits are bf16 values widened to fp32."""
+        if self.multi_token_handler != "first":
+            raise NotImplementedError("the fused kernel implements multi_token_handler='first' "
+                                      "(the reference default, trainer/verb.py:441)")
+        if not hidden_last.is_cuda:
+            raise RuntimeError("score_hidden runs on the GPU only (no CPU fallback)")
+        lib = _lib.load()
+        dev = hidden_last.device
+        h = hidden_last.to(torch.bfloat16).contiguous()
+        w = lm_head_weight.to(torch.bfloat16).contiguous()
+        ids, mask = self._device_params(dev)
+        B, H = h.shape
+        C, W = ids.shape
+        out = torch.empty(B, C, dtype=torch.float32, device=dev)
+        _lib.check(lib.lrb_verbalizer_score(_lib.ptr(h), _lib.ptr(w), B, H, w.shape[0], _lib.ptr(ids), _lib.ptr(mask),
+                                            C, W, 1 if self.post_log_softmax else 0,
+                                            1 if round_logits_to_bf16 else 0, _lib.ptr(out), _lib.stream_handle()))
+        return out
+
+    # ---- reference-compatible path on precomputed logits (trainer/verb.py:524-614) -----------------
+    def project(self, logits: torch.Tensor) -> torch.Tensor:
+        dev = logits.device
+        picked = logits[:, self.label_words_ids.to(dev)]                    # [B, C, W, T]
+        tok_mask = self.words_ids_mask.to(dev)
+        if self.multi_token_handler == "first":
+            picked = picked[..., 0]
+        elif self.multi_token_handler == "max":
+            picked = (picked - 1000 * (1 - tok_mask.unsqueeze(0))).max(dim=-1).values
+        elif self.multi_token_handler == "mean":
+            picked = (picked * tok_mask.unsqueeze(0)).sum(-1) / (tok_mask.unsqueeze(0).sum(-1) + 1e-15)
+        else:
+            raise ValueError(f"multi_token_handler {self.multi_token_handler} not configured")
+        return picked - 10000 * (1 - self.label_words_mask.to(dev))
+
+    def process_logits(self, logits: torch.Tensor) -> torch.Tensor:
+        words = self.project(logits)
+        if self.post_log_softmax:
+            B = words.shape[0]
+            probs = torch.softmax(words.reshape(B, -1), dim=-1).reshape(words.shape)
+            words = torch.log(probs + 1e-15)
+        m = self.label_words_mask.to(words.device)
+        return (words * m).sum(-1) / m.sum(-1)

@@ -1,0 +1,34 @@
+"""CPU: the C-ABI library loads and exports every symbol include/llamarec_b200.h declares; the
+ctypes table covers the header; size queries (no GPU work) answer sensibly."""
+import ctypes
+import re
+
+from llamarec_b200 import _lib
+
+
+def header_functions():
+    src = open(_lib.HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(lrb_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_symbols_exported_and_bound():
+    names = header_functions()
+    assert len(names) >= 15
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} missing from the ctypes signature table"
+    for n in _lib.SIGNATURES:
+        assert n in names, f"{n} bound but not declared in the header"
+
+
+def test_size_queries_without_gpu():
+    lib = _lib.load()
+    assert lib.lrb_version() == 100
+    assert lib.lrb_excl_stride(50) == 52 and lib.lrb_excl_stride(200) == 204
+    assert lib.lrb_bias_blk_bytes(1683) == 7 * 8192
+    assert lib.lrb_encoder_weight_floats(2) == 128 + 2 * 66816
+    assert lib.lrb_encode_workspace_bytes(16, 200, 0) >= 16 * 200 * (64 * 2 + 256) * 4
+    assert isinstance(lib.lrb_last_error(), (bytes, type(None)))

@@ -1,0 +1,188 @@
+"""CPU: host-side logic -- state-dict compatibility, weight packing, the scan algorithm the CUDA kernel
+implements, synthetic-data generators, shard arithmetic, and the multi-rank plumbing under gloo."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from llamarec_b200 import LRURec, synth
+from llamarec_b200.packing import BLOCK_FLOATS, OFF_BLOCKS, pack_encoder_weights
+from llamarec_b200.sharded import ShardedRetriever, shard_range
+from oracle import lru_oracle as O
+
+
+def _args(n=400):
+    return SimpleNamespace(num_items=n, bert_hidden_units=64, bert_num_blocks=2, bert_dropout=0.2, bert_attn_dropout=0.2)
+
+
+def test_state_dict_matches_reference_keys(golden_sd):
+    m = LRURec(_args())
+    own = m.state_dict()
+    assert set(own.keys()) == set(golden_sd.keys())
+    for k in own:
+        assert own[k].shape == golden_sd[k].shape and own[k].dtype == golden_sd[k].dtype, k
+    m.load_state_dict(golden_sd)   # a reference checkpoint loads unchanged
+
+
+def test_no_cpu_fallback(golden_sd):
+    m = LRURec(_args())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.encode(torch.zeros(2, 20, dtype=torch.int64))
+
+
+def test_packing_layout(golden_sd):
+    blob = pack_encoder_weights(golden_sd)
+    assert blob.numel() == OFF_BLOCKS + 2 * BLOCK_FLOATS
+    p = "model.lru_blocks.1."
+    base = OFF_BLOCKS + BLOCK_FLOATS
+    lam, gamma = O.lru_constants(golden_sd[p + "lru_layer.params_log"])
+    assert torch.allclose(blob[base:base + 128], lam.real.reshape(-1))
+    assert torch.allclose(blob[base + 256:base + 384], gamma.reshape(-1))
+    win_t = blob[base + 384: base + 384 + 64 * 256].reshape(64, 256)
+    w = golden_sd[p + "lru_layer.in_proj.weight"]
+    assert torch.equal(win_t[5, 2 * 17], w.real[17, 5]) and torch.equal(win_t[5, 2 * 17 + 1], w.imag[17, 5])
+    off = base + 384 + 64 * 256 + 256
+    wout_t = blob[off: off + 256 * 64].reshape(256, 64)
+    wo = golden_sd[p + "lru_layer.out_proj.weight"]
+    assert torch.equal(wout_t[2 * 9, 3], wo.real[3, 9]) and torch.equal(wout_t[2 * 9 + 1, 3], -wo.imag[3, 9])
+    # the packed real-arithmetic form reproduces the complex layer on a random vector
+    x = torch.randn(64)
+    bu_ref = torch.nn.functional.linear(x.to(torch.cfloat), w, golden_sd[p + "lru_layer.in_proj.bias"]) * gamma
+    b_in = blob[base + 384 + 64 * 256: base + 384 + 64 * 256 + 256]
+    bu = (x @ win_t + b_in).reshape(128, 2) * gamma.reshape(128, 1)
+    assert torch.allclose(torch.view_as_complex(bu.contiguous()), bu_ref.reshape(-1), atol=1e-6)
+
+
+def fenwick_scan(bu, lam, mask, L):
+    """numpy transliteration of lru_scan_kernel (llamarec_b200/csrc/encode.cu)."""
+    B, Lp, H = bu.shape
+    levels = int(np.log2(Lp))
+    off = Lp - L
+    out = np.zeros_like(bu)
+    for b in range(B):
+        q = np.zeros((levels, H), dtype=np.complex64)
+        for t in range(L):
+            pos = t + off
+            acc = bu[b, pos].copy()
+            snap, z, below = None, -1, True
+            for l in range(levels):
+                if (pos >> l) & 1:
+                    acc = acc + q[l]
+                elif below:
+                    snap, z, below = acc.copy(), l, False
+            out[b, pos] = acc
+            m = 1.0 if mask[b, pos] else 0.0
+            for l in range(levels):
+                x = snap * m if l == z else q[l]
+                q[l] = (x * lam).astype(np.complex64)
+    return out
+
+
+@pytest.mark.parametrize("L", [1, 5, 20, 37, 50, 64, 200])
+def test_kernel_scan_algorithm_equals_tree_scan_for_any_mask(L):
+    rng = np.random.default_rng(L)
+    Lp = 1 << int(np.ceil(np.log2(L))) if L > 1 else 1
+    B, H = 3, 8
+    bu = (rng.standard_normal((B, Lp, H)) + 1j * rng.standard_normal((B, Lp, H))).astype(np.complex64)
+    lam = (0.9 * np.exp(1j * rng.uniform(0, 6.28, H))).astype(np.complex64)
+    mask = rng.random((B, Lp)) < 0.7
+    mask[:, : Lp - L] = False
+    if Lp == 1:
+        return
+    ref = O.tree_scan(torch.from_numpy(bu), torch.from_numpy(lam).reshape(1, H), torch.from_numpy(mask)).numpy()
+    got = fenwick_scan(bu, lam, mask, L)
+    assert np.abs(ref[:, Lp - L:] - got[:, Lp - L:]).max() < 1e-5
+
+
+def test_synth_is_deterministic_and_left_padded():
+    cfg = synth.CONFIGS["c2_beauty"]
+    a, la = synth.make_sequences(cfg, num_users=50, seed=42)
+    b, lb = synth.make_sequences(cfg, num_users=50, seed=42)
+    assert torch.equal(a, b) and torch.equal(la, lb)
+    nz = a > 0
+    assert torch.all(nz[:, 1:] >= nz[:, :-1])            # zeros only on the left
+    assert a.max() <= cfg.num_items and la.min() >= 1
+    ids, lab = synth.make_sequences_fast(64, 10_000_000, 50)
+    assert ids.shape == (64, 50) and int(ids.max()) <= 10_000_000
+    sd = synth.make_state_dict(100)
+    assert sd["model.lru_blocks.0.lru_layer.in_proj.weight"].dtype == torch.complex64
+
+
+def test_shard_range_covers_everything():
+    for n in (1, 7, 1683, 10_000_001):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+class OracleBackend:
+    """Test-only backend: the CPU oracle restricted to a row range (stands in for the CUDA kernels)."""
+
+    def __init__(self, sd, rank, world):
+        self.sd = sd
+        n = sd["embedding.token.weight"].shape[0]
+        self.lo, self.hi = shard_range(n, rank, world)
+
+    def encode(self, x):
+        return O.encode(x, self.sd)
+
+    def local_topk(self, x, u, k, exclude_history):
+        s = u @ self.sd["embedding.token.weight"][self.lo:self.hi].t() + self.sd["model.bias"][self.lo:self.hi]
+        if exclude_history:
+            for b in range(x.shape[0]):
+                for i in x[b].tolist() + [0]:
+                    if self.lo <= i < self.hi:
+                        s[b, i - self.lo] = -1e9
+        ts, ti = O.topk_sorted(s, k)
+        return ts, (ti + self.lo).to(torch.int32)
+
+    def merge(self, s_all, i_all, k, labels, ks):
+        R, B, K = s_all.shape
+        s = s_all.permute(1, 0, 2).reshape(B, R * K)
+        i = i_all.permute(1, 0, 2).reshape(B, R * K).to(torch.int64)
+        key = torch.argsort(i, dim=1, stable=True)                      # id asc ...
+        s, i = s.gather(1, key), i.gather(1, key)
+        order = torch.argsort(-s.double(), dim=1, stable=True)[:, :k]   # ... then score desc (stable)
+        return {"scores": s.gather(1, order), "ids": i.gather(1, order).to(torch.int32)}
+
+
+def _worker(rank, world, port, sd_np, ids_np, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sd = {k: torch.from_numpy(v) for k, v in sd_np.items()}
+    x = torch.from_numpy(ids_np)
+    r = ShardedRetriever(OracleBackend(sd, rank, world))
+    out = r.retrieve(x, k=20, exclude_history=True)
+    if rank == 0:
+        q.put((out["scores"].numpy(), out["ids"].numpy(), out["u"].numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_retrieval_two_ranks_gloo(golden_sd):
+    ids = np.load(os.path.join(ROOT, "tests", "golden", "lru_case_left_l20.npz"))["ids"][:11]   # odd batch
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    sd_np = {k: v.numpy() for k, v in golden_sd.items()}
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, sd_np, ids, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    s, i, u = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x = torch.from_numpy(ids)
+    ref_s, ref_i = O.retrieve(x, golden_sd, 20)
+    np.testing.assert_allclose(u, O.encode(x, golden_sd).numpy(), atol=1e-6)
+    assert np.array_equal(i, ref_i.numpy().astype(np.int32))
+    np.testing.assert_allclose(s, ref_s.numpy(), atol=1e-6)

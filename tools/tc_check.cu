@@ -32,6 +32,7 @@
   } while (0)
 
 extern "C" void lrb_debug_set_score_mode(int m);
+extern "C" void lrb_debug_set_stats(long long* p);
 
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
@@ -304,6 +305,33 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
   float ms;
   CK(cudaEventElapsedTime(&ms, e0, e1));
   ms /= iters;
+  {
+    // one more launch with per-CTA statistics
+    int sms = 0, cc = 0;
+    lrb_device_info(&sms, &cc);
+    long long* dstats;
+    CK(cudaMalloc(&dstats, sms * 8 * sizeof(long long)));
+    CK(cudaMemset(dstats, 0, sms * 8 * sizeof(long long)));
+    lrb_debug_set_stats(dstats);
+    LK(lrb_score_topk(du, T.e16, T.bias_pad, bblk, B, rows, 0, with_excl ? dex : nullptr, with_excl ? dbl : nullptr,
+                      stride, K, 0, dps, dpi, dpc, slots, scratch, nullptr));
+    CK(cudaDeviceSynchronize());
+    lrb_debug_set_stats(nullptr);
+    std::vector<long long> st(sms * 8);
+    CK(cudaMemcpy(st.data(), dstats, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    printf("  per-CTA [cycles(M) appends/thread compactions/warp tiles] for CTAs 0,1,64,127,128,137,147:\n");
+    int show[7] = {0, 1, 64, 127, 128, 137, 147};
+    for (int i = 0; i < 7; ++i) {
+      int c = show[i];
+      if (c >= sms) continue;
+      printf("   cta %3d: %.2f  %.1f  %.1f  %lld | epi-warp0: wait %.2fM compact %.2fM first64tiles %.2fM\n", c, st[c * 4] / 1e6, st[c * 4 + 1] / 256.0, st[c * 4 + 2] / 8.0, st[c * 4 + 3],
+             st[sms * 4 + c * 4] / 1e6, st[sms * 4 + c * 4 + 1] / 1e6, st[sms * 4 + c * 4 + 2] / 1e6);
+    }
+    long long mn = 1LL << 62, mx = 0; double sum = 0;
+    for (int c = 0; c < sms; ++c) { mn = std::min(mn, st[c * 4]); mx = std::max(mx, st[c * 4]); sum += st[c * 4]; }
+    printf("   cycles min %.2fM max %.2fM mean %.2fM\n", mn / 1e6, mx / 1e6, sum / sms / 1e6);
+    cudaFree(dstats);
+  }
   double tflops = 2.0 * B * (double)rows * 64 / (ms * 1e-3) / 1e12;
   printf("[time] B=%d rows=%d K=%d bias=%d excl=%d slots=%d : %.3f ms/iter  %.1f TFLOP/s  %.0f users/s\n", B, rows, K,
          (int)with_bias, (int)with_excl, slots, ms, tflops, B / (ms * 1e-3));
