@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: users/sec for LRURec encode + full-catalogue score + top-20 (BASELINE.json metric)
+on the scaled synthetic catalogue (configs[3]: 10M items, d=64, batch 4096, L=50), on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of 4096 synthetic users: sequence preparation,
+encoder, catalogue scoring fused with top-20, k-way merge + metrics.  With N > 1 the item table is
+row-sharded over the ranks (strong scaling: the batch and the catalogue are fixed), the encoder is
+batch-sharded, and two all-gathers (user states, local top-20 lists) connect them.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference's path on the
+host cores instead (the reference is pure Python/PyTorch; /root/reference is not on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ITEMS = 10_000_000
+BATCH = 4096
+MAX_LEN = 50
+TOPK = 20
+CPU_SAMPLE_USERS = 256
+WORKLOAD = "c4_10m: 10M items, d=64, batch 4096, max_len 50, top-20 (BASELINE.json configs[3])"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def model_args(n_items):
+    return SimpleNamespace(num_items=n_items, bert_hidden_units=64, bert_num_blocks=2, bert_dropout=0.2,
+                           bert_attn_dropout=0.2)
+
+
+def make_inputs():
+    from llamarec_b200 import synth
+    return synth.make_sequences_fast(BATCH, N_ITEMS, MAX_LEN, seed=42)
+
+
+def build_product_model(device):
+    from llamarec_b200 import LRURec, synth
+    sd = synth.make_state_dict(1000, seed=42)                     # encoder weights (random init, reference shapes)
+    table, bias = synth.make_table_bf16(N_ITEMS, seed=42, device=device)   # trunc-normal table, zero bias
+    m = LRURec(model_args(N_ITEMS))
+    m.load_state_dict({k: v for k, v in sd.items() if k not in ("embedding.token.weight", "model.bias")}, strict=False)
+    m = m.to(device).eval()
+    with torch.no_grad():
+        m.embedding.token.weight.copy_(table)
+        m.model.bias.copy_(bias)
+    del table
+    return m, sd
+
+
+def cpu_oracle_run(sd, table_cpu, bias_cpu, ids, users):
+    """The reference's path restated for the CPU: encode -> chunked last-position scoring with a running
+    top-20 (the reference forward cannot allocate [B, L, N+1] at this size)."""
+    from oracle import lru_oracle as O
+    sd_full = dict(sd)
+    sd_full["embedding.token.weight"] = table_cpu
+    sd_full["model.bias"] = bias_cpu
+    x = ids[:users]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.retrieve(x, sd_full, TOPK, exclude_history=True, chunk=65536)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from llamarec_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ids, _ = make_inputs()
+    sd = synth.make_state_dict(1000, seed=42)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    table, bias = synth.make_table_bf16(N_ITEMS, seed=42, device=dev)
+    table, bias = table.cpu(), bias.cpu()
+    times = []
+    for s in range(args.warmup + args.steps):
+        dt = cpu_oracle_run(sd, table, bias, ids, CPU_SAMPLE_USERS)
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = CPU_SAMPLE_USERS * len(times) / total
+    sample = f"{CPU_SAMPLE_USERS} of the {BATCH} users per step against the full 10M-item table (fp32, chunked 65536 items)"
+    line = {
+        "impl": "reference", "metric": "users_per_sec_encode_score_top20", "value": value, "unit": "users/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "max_len": MAX_LEN, "k": TOPK},
+        "cpu_baseline": {"value": value, "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_product(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from llamarec_b200.sharded import CudaBackend, ShardedRetriever, shard_range
+
+    assert torch.cuda.is_available(), "bench.py (product arm) needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    model, sd = build_product_model(device)
+    ids_host, labels_host = make_inputs()
+    ids_pinned = ids_host.pin_memory()
+    ids_dev = ids_host.to(device)
+    labels_dev = labels_host.to(device)
+    ks = [1, 5, 10, 20]
+
+    if world > 1:
+        retr = ShardedRetriever(CudaBackend(model, rank, world, precision="bf16"))
+        step = lambda x: retr.retrieve(x, k=TOPK, exclude_history=True, labels=labels_dev, ks=ks)
+        rows = shard_range(N_ITEMS + 1, rank, world)
+        local_rows = rows[1] - rows[0]
+    else:
+        step = lambda x: model.retrieve(x, k=TOPK, exclude_history=True, labels=labels_dev, ks=ks, precision="bf16")
+        local_rows = N_ITEMS + 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(ids_dev)
+    barrier()
+
+    # ---- device-resident timing (value) ----
+    model.profile_events = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(ids_dev)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    score_ms = [a.elapsed_time(b) for a, b in model.profile_events]
+    model.profile_events = None
+
+    # ---- end-to-end through the public API with host buffers ----
+    out_ids_host = torch.empty(BATCH, TOPK, dtype=torch.int32).pin_memory()
+    out_scores_host = torch.empty(BATCH, TOPK, dtype=torch.float32).pin_memory()
+    sums_host = torch.empty(len(ks), 3, dtype=torch.float32).pin_memory()
+    ids_stage = torch.empty_like(ids_dev)
+
+    def e2e_step():
+        ids_stage.copy_(ids_pinned, non_blocking=True)
+        o = step(ids_stage)
+        out_ids_host.copy_(o["ids"], non_blocking=True)
+        out_scores_host.copy_(o["scores"], non_blocking=True)
+        sums_host.copy_(o["metric_sums"], non_blocking=True)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s, statistics.mean(score_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s, score_ms_mean = t.tolist()
+
+    if rank != 0:
+        return
+    pk = peaks()
+    ms_per_step = ms_total / args.steps
+    value = BATCH * args.steps / (ms_total * 1e-3)
+    e2e_value = BATCH * args.steps / e2e_s
+    flops = 2.0 * BATCH * local_rows * 64                       # algorithmic FLOPs of one scoring launch
+    achieved = flops / (score_ms_mean * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("score_topk_tc_dram_bytes_per_launch")
+        except (ValueError, OSError):
+            traffic = None
+    line = {
+        "metric": "users_per_sec_encode_score_top20", "value": value, "unit": "users/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "max_len": MAX_LEN, "k": TOPK,
+                   "parallelism": f"row-sharded item table x{world}, batch-sharded encoder" if world > 1 else "single GPU",
+                   "l2": "item table (1.28 GB bf16) is 10x larger than L2; no flush needed",
+                   "scoring_operands": "bf16 table and user state, fp32 accumulate (tcgen05); encoder fp32"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": ids_pinned.numel() * 8,
+                "d2h_bytes_per_step": BATCH * TOPK * 8 + len(ks) * 3 * 4},
+        "gpu_launches": args.steps * (2 + 6 + 1 + 1 + (1 if world > 1 else 0)),
+        "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": achieved,
+                     "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
+                     "peak_source": pk["source"] + " (sustained bf16)", "kernel_ms": score_ms_mean,
+                     "kernel_share_of_step": score_ms_mean / ms_per_step},
+    }
+    if world == 1 and not args.skip_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        table_cpu = model.embedding.token.weight.detach().float().cpu()
+        bias_cpu = model.model.bias.detach().float().cpu()
+        dt = cpu_oracle_run(sd, table_cpu, bias_cpu, ids_host, CPU_SAMPLE_USERS)
+        line["cpu_baseline"] = {
+            "value": CPU_SAMPLE_USERS / dt, "unit": "users/s", "cores": cores, "kind": "port",
+            "sample": f"{CPU_SAMPLE_USERS} of the {BATCH} users against the full 10M-item table, one pass "
+                      f"({dt:.1f} s; oracle port of model/lru.py + chunked scoring + running top-20)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true",
+                    help="profiling convenience: omit the ~20 s CPU oracle leg (the default run includes it)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    try:
+        run_product(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

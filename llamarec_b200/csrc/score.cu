@@ -274,9 +274,13 @@ int lrb_score_topk_slots(int B, int64_t rows, int precision, int* slots) {
   return LRB_OK;
 }
 
-static size_t gthr_bytes(int B) {
+// worst-case slot count is 2 * (number of SMs + 2): reserve that so the size depends on B only
+static size_t gslots_bytes(int B) {
+  int sms = lrb::device_sm_count();
+  if (sms <= 0) sms = 148;
   const size_t m_tiles = (static_cast<size_t>(B) + lrb::tc::BM - 1) / lrb::tc::BM;
-  return (m_tiles * lrb::tc::BM * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  const size_t max_slots = 2 * (static_cast<size_t>(sms) / m_tiles + 2);
+  return (m_tiles * lrb::tc::BM * max_slots * sizeof(int) + 255) & ~static_cast<size_t>(255);
 }
 
 size_t lrb_score_scratch_bytes(int B) {
@@ -284,7 +288,7 @@ size_t lrb_score_scratch_bytes(int B) {
   if (sms <= 0) sms = 148;
   const size_t ring = static_cast<size_t>(sms) * lrb::tc::EPI_THREADS * lrb::tc::RING_GROUPS *
                       lrb::tc::RING_REC_BYTES;
-  return gthr_bytes(B) + ring;
+  return gslots_bytes(B) + ring;
 }
 
 int lrb_score_topk(const void* u, const void* table, const float* bias_pad, const void* bias_blk,
@@ -335,13 +339,18 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
   p.row_offset = static_cast<int>(row_offset); p.K = K;
   p.bias_blk = static_cast<const uint8_t*>(bias_blk);
   p.excl_sorted = excl_sorted; p.excl_bloom = excl_bloom; p.excl_stride = excl_stride;
-  p.gthr = static_cast<int*>(scratch);
-  p.ring = static_cast<uint8_t*>(scratch) + gthr_bytes(B);
+  p.gslots = static_cast<int*>(scratch);
+  p.ring = static_cast<uint8_t*>(scratch) + gslots_bytes(B);
+  {
+    // entries each of the 2*s_full full-stream threads of a user must hold for the union bound
+    const int c = d.s_full > 0 ? (K + 2 * d.s_full - 1) / (2 * d.s_full) : 99;
+    p.c_share = c <= 4 ? c : 0;
+  }
   p.part_scores = part_scores; p.part_ids = part_ids; p.part_cnt = part_cnt; p.slots = d.slots;
   p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
   LRB_CUDA_TRY(cudaMemsetAsync(part_cnt, 0, static_cast<size_t>(B) * d.slots * sizeof(int), st));
-  LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, gthr_bytes(B), st));
+  LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, static_cast<size_t>(d.m_tiles) * tc::BM * d.slots * sizeof(int), st));
   if (K <= 20) return launch_tc<20, 3, false>(ta, tb, p, d.grid, st);
   if (K <= 32) return launch_tc<32, 3, false>(ta, tb, p, d.grid, st);
   return launch_tc<50, 2, false>(ta, tb, p, d.grid, st);
@@ -386,7 +395,7 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
   p.B = static_cast<int>(M); p.m_tiles = d.m_tiles; p.rows = static_cast<int>(rows); p.n_tiles = d.n_tiles;
   p.row_offset = 0; p.K = 1; p.bias_blk = static_cast<const uint8_t*>(bias_blk);
   p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
-  p.gthr = nullptr; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
+  p.gslots = nullptr; p.c_share = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
   p.dense_out = out; p.dense_ld = ld_out; p.debug_mode = 0; p.debug_stats = nullptr;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
   return launch_tc<20, 3, true>(ta, tb, p, d.grid, st);

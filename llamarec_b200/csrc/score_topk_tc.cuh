@@ -46,7 +46,12 @@ struct ScoreParams {
   const int* excl_sorted;      // [B][excl_stride] ascending global ids, INT_MAX padded; null = none
   const uint32_t* excl_bloom;  // [B][4] 128-bit membership filter over (id & 127)
   int excl_stride;
-  int* gthr;                   // [m_tiles*128] ordered-int shared lower bounds (memset 0x80)
+  int* gslots;                 // [m_tiles*128][slots] ordered-int keys: each FULL-stream thread's c-th best
+                               // score so far (memset 0x80 = unset).  The 2*s_full full-stream slots of a
+                               // user all start at t = 0; with c * 2*s_full >= K the minimum over them is a
+                               // valid lower bound on the user's K-th best (union bound), also used by the
+                               // shared-stream CTAs, whose own slots are ignored (they may start late).
+  int c_share;                 // c (1..4); 0 disables the union bound
   uint8_t* ring;               // [gridDim.x][EPI_THREADS][RING_GROUPS][RING_REC_BYTES] candidate rings
   float* part_scores;          // [B][slots][K]
   int* part_ids;               // [B][slots][K]
@@ -205,6 +210,22 @@ __device__ __noinline__ float topk_consider(float s, int gid, int row_limit_gid,
 constexpr int RING_GROUPS = 16;
 constexpr int RING_REC_BYTES = 80;   // 16 fp32 + int32 gid0, padded to a multiple of 16 B
 
+// c-th largest score of an unsorted set (1 <= c <= 4); -inf if the set holds fewer than c entries.
+template <int STRIDE>
+LRB_DEVINL float set_cth_best(uint32_t ls, uint32_t ln, int c) {
+  const int n = lds_s32(ln);
+  float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY;   // running top-4, descending
+  for (int i = 0; i < n; ++i) {
+    float v = lds_f32(ls + i * STRIDE * 4);
+    float t;
+    t = fminf(m1, v); m1 = fmaxf(m1, v); v = t;
+    t = fminf(m2, v); m2 = fmaxf(m2, v); v = t;
+    t = fminf(m3, v); m3 = fmaxf(m3, v); v = t;
+    m4 = fmaxf(m4, v);
+  }
+  return c == 1 ? m1 : (c == 2 ? m2 : (c == 3 ? m3 : m4));
+}
+
 struct RingRec {
   float4 a, b, c, d;
   int gid0;
@@ -224,7 +245,7 @@ LRB_DEVINL RingRec load_rec(const float4* ring, int g, bool act) {
 }
 
 template <int STRIDE>
-__device__ __noinline__ float compact_ring(const float4* ring, int cnt, float own_thr,
+__device__ __noinline__ float compact_ring(const float4* ring, int cnt, float own_thr, float shared_thr,
                                            int row_limit_gid, uint32_t ls, uint32_t li, uint32_t ln,
                                            int K, const int* excl, uint32_t excl_s, int excl_stride,
                                            uint32_t bloom0, uint32_t bloom1, uint32_t bloom2,
@@ -250,7 +271,7 @@ __device__ __noinline__ float compact_ring(const float4* ring, int cnt, float ow
         best = gt ? s[j] : best;
         bj = gt ? j : bj;
       }
-      const bool pass = act && best > -INFINITY && best >= own_thr;
+      const bool pass = act && best > -INFINITY && best >= fmaxf(own_thr, shared_thr);
       if (!__any_sync(0xffffffffu, pass)) break;
       if (pass) {
         const int gid = gid0 + bj;
@@ -281,7 +302,7 @@ struct SmemLayout {
   static constexpr int kListI = kListS + KMAX * EPI_THREADS * 4;
   static constexpr int kListN = kListI + KMAX * EPI_THREADS * 4;
   static constexpr int kRowThr = kListN + EPI_THREADS * 8;
-  static constexpr int kExcl = kRowThr + BM * 4;
+  static constexpr int kExcl = kRowThr + 2 * BM * 4 + 16;   // two threshold buffers + service-warp flags
   static constexpr int kBars = kExcl + (kExclSmem ? BM * EX_CAP * 4 : 0);
   // barriers: full[NS], empty[NS], tmem_full[2], tmem_empty[2], a_full, a_empty
   static constexpr int kNumBars = 2 * NS + 2 * ACC_STAGES + 2;
@@ -319,7 +340,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   float* sListS = reinterpret_cast<float*>(smem + L::kListS);
   int* sListI = reinterpret_cast<int*>(smem + L::kListI);
   int* sListN = reinterpret_cast<int*>(smem + L::kListN);
-  int* sRowThr = reinterpret_cast<int*>(smem + L::kRowThr);
+  int* sRowThr = reinterpret_cast<int*>(smem + L::kRowThr);          // [2][BM] double-buffered by segment parity
+  volatile int* sSvc = reinterpret_cast<volatile int*>(smem + L::kRowThr + 2 * BM * 4);  // {cur_m, cur_seg, done}
   int* sExcl = reinterpret_cast<int*>(smem + L::kExcl);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
   uint64_t* full_bar = bars;
@@ -354,6 +376,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     mbar_init(a_full_bar, 1);
     mbar_init(a_empty_bar, 1);
     mbar_fence_init();
+    sSvc[0] = -1; sSvc[1] = -1; sSvc[2] = 0;
   }
   if (warp == 2) {
     tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -440,6 +463,32 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         ++seg_idx;
       }
     }
+  } else if (warp == 3) {
+    // ===================== threshold service =====================
+    // Background refresh of the per-row union bound: min over the row's stream slots of the published
+    // c-th best scores (valid lower bound on the row's K-th best because c * slots >= K).  Written
+    // into the threshold buffer of the segment it was computed for; a segment switch in between is
+    // detected by re-reading the segment counter right before the write.
+    if (!kDense && p.c_share > 0) {
+      while (sSvc[2] == 0) {
+        const int seg = sSvc[1];
+        const int m = sSvc[0];
+        if (seg >= 0) {
+          for (int rr = lane; rr < BM; rr += 32) {
+            const int b = m * BM + rr;
+            if (b >= p.B) continue;
+            const volatile int* gs = p.gslots + static_cast<size_t>(b) * p.slots;
+            int mn = INT_MAX;
+            for (int sl = 0; sl < 2 * p.s_full; ++sl) {
+              const int v = gs[sl];
+              mn = v < mn ? v : mn;
+            }
+            if (mn > static_cast<int>(0x80808080) && sSvc[1] == seg) atomicMax(&sRowThr[(seg & 1) * BM + rr], mn);
+          }
+        }
+        __nanosleep(2000);
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;          // 0..7
@@ -455,14 +504,19 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     Segment sg;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int seg_idx = -1;
     while (walk.next(sg)) {
+      ++seg_idx;
       const int b = sg.m * BM + r;
       const bool live = b < p.B;
+      int* rowthr = sRowThr + (seg_idx & 1) * BM;
       // per-segment state reset
       sts_s32(ln, 0);
       float own_thr = -INFINITY;
       int published = INT_MIN;
-      if (half == 0) sRowThr[r] = INT_MIN;
+      if (half == 0) rowthr[r] = INT_MIN;
+      const int my_slot = sg.slot * 2 + half;
+      const bool publishes = sg.slot < p.s_full;   // only full-stream threads feed the union bound
       const int* excl = nullptr;
       uint32_t bloom0 = 0u, bloom1 = 0u, bloom2 = 0u, bloom3 = 0u;
       if (!kDense && live && p.excl_sorted != nullptr) {
@@ -484,12 +538,40 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         excl_s = smem_u32(sExcl + r * EX_CAP);
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // sRowThr reset / sExcl visible
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // threshold buffer reset / sExcl visible
+      if (et == 0) {
+        sSvc[0] = sg.m;
+        __threadfence_block();
+        sSvc[1] = seg_idx;      // the service warp starts refreshing this segment's buffer
+      }
       int cnt = 0;   // records waiting in this thread's ring
-      int k_glb = INT_MIN;   // shared lower bound, fetched one tile ahead of its use
+      bool boot = !kDense;   // warp-uniform: the first compaction of a segment happens after one chunk
       float4* ring = reinterpret_cast<float4*>(
           p.ring + (static_cast<size_t>(blockIdx.x) * EPI_THREADS + et) * (RING_GROUPS * RING_REC_BYTES));
       const int limit_gid = p.row_offset + p.rows;
+
+      // lock-step drain of the warp's rings + publication of the improved bounds
+      auto drain = [&]() {
+        float shared_thr = -INFINITY;
+        if (live) {
+          const int kk = *reinterpret_cast<volatile int*>(rowthr + r);
+          if (kk != INT_MIN) shared_thr = key_to_float(kk);
+        }
+        own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, shared_thr, limit_gid, ls, li, ln, p.K, excl,
+                                            excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
+        cnt = 0;
+        if (live) {
+          if (own_thr > -INFINITY) atomicMax(&rowthr[r], float_to_key(own_thr));   // sibling column half
+          if (p.c_share > 0 && publishes) {
+            const float cb = set_cth_best<EPI_THREADS>(ls, ln, p.c_share);
+            const int key = float_to_key(cb);
+            if (cb > -INFINITY && key > published) {
+              published = key;
+              p.gslots[static_cast<size_t>(b) * p.slots + my_slot] = key;   // monotone, single writer
+            }
+          }
+        }
+      };
 
       for (int n = sg.n0; n < sg.n1; ++n) {
 #ifdef LRB_DEBUG_MODES
@@ -505,11 +587,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // rows beyond B never produce candidates: their threshold is +inf
         float t_eff = live ? own_thr : INFINITY;
         if (!kDense && live) {
-          const int k_row = sRowThr[r];
-          const int kk = k_row > k_glb ? k_row : k_glb;
+          const int kk = *reinterpret_cast<volatile int*>(rowthr + r);
           if (kk != INT_MIN) t_eff = fmaxf(own_thr, key_to_float(kk));
-          // issue the load for the NEXT tile now; its latency hides behind this tile's work
-          k_glb = *reinterpret_cast<volatile int*>(p.gthr + b);
         }
 
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
@@ -517,6 +596,116 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int col_gid0 = p.row_offset + n * BN + half * (BN / 2);
 
 #ifdef LRB_DEBUG_MODES
+        if (p.debug_mode >= 50 && p.debug_mode <= 53) {
+          // math-only probe: one x32 load per tile, the max-tree + compare executed 4 times on it
+          uint32_t w0[32];
+          tmem_ld_32x32(taddr, w0);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          int hits = 0;
+          const int nrep = p.debug_mode == 52 ? 2 : (p.debug_mode == 53 ? 4 : 1);
+          for (int rep = 0; rep < nrep; ++rep)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float gm[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float q[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(w0[g * 16 + j] ^ static_cast<uint32_t>(c + 4 * rep));
+              const float m1 = max3(q[0], q[1], q[2]);
+              const float m2 = max3(q[3], q[4], q[5]);
+              const float m3 = max3(q[6], q[7], q[8]);
+              const float m4 = max3(q[9], q[10], q[11]);
+              const float m5 = max3(q[12], q[13], q[14]);
+              gm[g] = fmaxf(max3(m1, m2, m3), max3(m4, m5, q[15]));
+            }
+            if (p.debug_mode == 51) {
+              if (fmaxf(gm[0], gm[1]) >= t_eff + 1e30f) ++hits;      // never true: branch per chunk
+            } else {
+              hits += (fmaxf(gm[0], gm[1]) >= t_eff + 1e30f) ? 1 : 0;
+            }
+          }
+          if (hits == 12345) p.gslots[0] = 1;
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        if (p.debug_mode >= 20) {
+          // 5 repetitions of the tile's four x32 loads with 1 (mode 20), 4 (mode 30) loads in flight,
+          // or eight x16 loads with 2 in flight (mode 40)
+          uint32_t acc_x = 0;
+          for (int rep = 0; rep < 5; ++rep) {
+            if (p.debug_mode == 20) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint32_t w0[32];
+                tmem_ld_32x32(taddr + c * 32, w0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc_x ^= w0[j];
+              }
+            } else if (p.debug_mode == 30) {
+              uint32_t w0[32], w1[32], w2[32], w3[32];
+              tmem_ld_32x32(taddr, w0);
+              tmem_ld_32x32(taddr + 32, w1);
+              tmem_ld_32x32(taddr + 64, w2);
+              tmem_ld_32x32(taddr + 96, w3);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j] ^ w2[j] ^ w3[j];
+            }
+          }
+          if (acc_x == 0x12345678u) p.gslots[0] = 1;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        if (p.debug_mode >= 10) {
+          // repeat the four x32 loads (debug_mode - 9) times per tile: measures TMEM->RF bandwidth
+          const int reps = p.debug_mode - 9;
+          uint32_t acc_x = 0;
+          for (int rep = 0; rep < reps; ++rep) {
+            uint32_t w0[32], w1[32];
+            tmem_ld_32x32(taddr, w0);
+            tmem_ld_32x32(taddr + 32, w1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j];
+            tmem_ld_32x32(taddr + 64, w0);
+            tmem_ld_32x32(taddr + 96, w1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j];
+          }
+          if (acc_x == 0x12345678u) p.gslots[0] = 1;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        if (p.debug_mode == 4) {
+          // all four loads in flight, one wait: separates TMEM-load latency from bandwidth
+          uint32_t w0[32], w1[32], w2[32], w3[32];
+          tmem_ld_32x32(taddr, w0);
+          tmem_ld_32x32(taddr + 32, w1);
+          tmem_ld_32x32(taddr + 64, w2);
+          tmem_ld_32x32(taddr + 96, w3);
+          tmem_ld_wait();
+          uint32_t acc_x = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j] ^ w2[j] ^ w3[j];
+          if (acc_x == 0x12345678u) p.gslots[0] = 1;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         if (p.debug_mode == 2 || p.debug_mode == 3) {
           if (p.debug_mode == 3) {
             uint32_t w[32];
@@ -528,7 +717,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc_x ^= w[j];
             }
-            if (acc_x == 0x12345678u) p.gthr[0] = 1;   // keep the loads alive
+            if (acc_x == 0x12345678u) p.gslots[0] = 1;   // keep the loads alive
           }
           tc_fence_before();
           __syncwarp();
@@ -605,24 +794,19 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (!kDense) {
           // uniform point, once per tile: a tile adds at most 8 records per thread, so draining
           // whenever some lane holds more than RING_GROUPS-8 keeps every ring within capacity.
-          if (__any_sync(0xffffffffu, cnt > RING_GROUPS - 8)) {
+          // The first tile of a segment always drains (bootstrap): every stream then holds K entries
+          // and publishes its c-th best within the first microseconds, which defines the union bound.
+          if (__any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0))) {
+            boot = false;
 #ifdef LRB_DEBUG_MODES
             dbg_appends += cnt;
             if (lane == 0) dbg_compactions += 1;
             const long long c0 = clock64();
 #endif
-            own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, limit_gid, ls, li, ln, p.K, excl,
-                                                excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
+            drain();
 #ifdef LRB_DEBUG_MODES
             dbg_compact += clock64() - c0;
 #endif
-            cnt = 0;
-            const int key = float_to_key(own_thr);
-            if (live && own_thr > -INFINITY && key > published) {
-              published = key;
-              atomicMax(&sRowThr[r], key);
-              atomicMax(p.gthr + b, key);
-            }
           }
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -632,12 +816,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       dbg_appends += cnt;
       if (lane == 0 && quad == 0 && half == 0) dbg_tiles += sg.n1 - sg.n0;
 #endif
-      if (!kDense) {
-        // final drain of this segment (whole warp, lock-step)
-        own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, limit_gid, ls, li, ln, p.K, excl,
-                                            excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
-        cnt = 0;
-      }
+      if (!kDense) drain();   // final drain of this segment (whole warp, lock-step)
 
       if (!kDense && live) {
         const int held = lds_s32(ln);
@@ -648,8 +827,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           p.part_ids[base * p.K + i] = lds_s32(li + i * EPI_THREADS * 4);
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // before the next segment resets sRowThr
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // before the next segment resets its buffer
     }
+    if (et == 0) sSvc[2] = 1;   // all segments of this CTA are done: stop the threshold service
   }
 
 #ifdef LRB_DEBUG_MODES

@@ -88,6 +88,8 @@ class LRURec(nn.Module):
         self._prepared_sig = None
         self._cache: Dict[str, torch.Tensor] = {}
         self._ws: Dict[tuple, torch.Tensor] = {}
+        # optional list; when set, retrieve() appends (start, end) CUDA events around the scoring launch
+        self.profile_events = None
         # row shard of the item table owned by this instance: [row_begin, row_end)
         self.row_begin, self.row_end = 0, vocab
 
@@ -162,12 +164,18 @@ class LRURec(nn.Module):
             uu, table, bias_blk = u, c["table_f32_shard"], None
         else:
             uu, table, bias_blk = u_bf16, c["table_bf16"], c["bias_blk"]
+        if self.profile_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         _lib.check(lib.lrb_score_topk(
             _lib.ptr(uu), _lib.ptr(table), _lib.ptr(c["bias_pad"]), _lib.ptr(bias_blk), B, rows, self.row_begin,
             _lib.ptr(seq["excl_sorted"]) if exclude_history else None,
             _lib.ptr(seq["excl_bloom"]) if exclude_history else None,
             seq["excl_stride"], k, prec, _lib.ptr(part_s), _lib.ptr(part_i), _lib.ptr(part_c), S,
             _lib.ptr(scratch), _lib.stream_handle()))
+        if self.profile_events is not None:
+            ev1.record()
+            self.profile_events.append((ev0, ev1))
         if not merge:
             return {"part_scores": part_s, "part_ids": part_i, "part_cnt": part_c, "u": u}
         out = merge_lists(part_s, part_i, part_c, k_out=k, labels=labels, ks=ks)
