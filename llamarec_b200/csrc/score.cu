@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(ROWS) score_f32_kernel(const Params p) {
         const int gid = p.row_offset + i0 + it;
         const int bw = (gid >> 5) & 3;
         const uint32_t bword = bw == 0 ? bloom0 : (bw == 1 ? bloom1 : (bw == 2 ? bloom2 : bloom3));
-        own_thr = tc::topk_consider<ROWS>(s, gid, limit_gid, own_thr, ls_a, li_a, ln_a, p.K, excl,
+        own_thr = tc::topk_consider<ROWS, LRB_MAX_K>(s, gid, limit_gid, own_thr, ls_a, li_a, ln_a, p.K, excl,
                                           p.excl_stride, bword);
       }
     }

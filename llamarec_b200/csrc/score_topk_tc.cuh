@@ -136,7 +136,7 @@ struct SegmentWalk {
 // Returns the thread's own K-th best score (-inf while the set is not full).
 // All pointers are 32-bit shared-space addresses.
 // -------------------------------------------------------------------------------------------
-template <int STRIDE>
+template <int STRIDE, int KMAX>
 LRB_DEVINL float topk_consider_inl(float s, int gid, int row_limit_gid, float own_thr,
                                    uint32_t ls, uint32_t li, uint32_t ln, int K,
                                    const int* excl, uint32_t excl_s, int excl_stride,
@@ -174,27 +174,40 @@ LRB_DEVINL float topk_consider_inl(float s, int gid, int row_limit_gid, float ow
     sts_f32(ls + wp * ES, s);
     sts_s32(li + wp * ES, gid);
   }
-  // rescan: worst = lowest score, ties broken towards the higher id
-  float m = lds_f32(ls);
-  int mi = lds_s32(li);
-  int mp = 0;
-#pragma unroll 4
-  for (int i = 1; i < K; ++i) {
-    const float v = lds_f32(ls + i * ES);
-    if (v <= m) {
-      const int vi = lds_s32(li + i * ES);
-      if (v < m || vi > mi) { m = v; mi = vi; mp = i; }
+  // rescan: worst = lowest score, ties broken towards the higher id.  All K score loads are issued
+  // back to back (independent), the minimum and its position are found without branches; ids are
+  // only consulted when the minimum is not unique (rare).
+  float v[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) v[i] = i < K ? lds_f32(ls + i * ES) : INFINITY;
+  float m = v[0];
+#pragma unroll
+  for (int i = 1; i < KMAX; ++i) m = fminf(m, v[i]);
+  int mp = 0, ties = 0;
+#pragma unroll
+  for (int i = KMAX - 1; i >= 0; --i) {
+    const bool eq = v[i] == m;
+    mp = eq ? i : mp;
+    ties += eq ? 1 : 0;
+  }
+  if (ties > 1) {
+    int mi = lds_s32(li + mp * ES);
+    for (int i = mp + 1; i < K; ++i) {
+      if (lds_f32(ls + i * ES) == m) {
+        const int vi = lds_s32(li + i * ES);
+        if (vi > mi) { mi = vi; mp = i; }
+      }
     }
   }
   sts_s32(ln + ES, mp);
   return m;
 }
 
-template <int STRIDE>
+template <int STRIDE, int KMAX>
 __device__ __noinline__ float topk_consider(float s, int gid, int row_limit_gid, float own_thr,
                                             uint32_t ls, uint32_t li, uint32_t ln, int K,
                                             const int* excl, int excl_stride, uint32_t bloom_word) {
-  return topk_consider_inl<STRIDE>(s, gid, row_limit_gid, own_thr, ls, li, ln, K, excl, 0u, excl_stride,
+  return topk_consider_inl<STRIDE, KMAX>(s, gid, row_limit_gid, own_thr, ls, li, ln, K, excl, 0u, excl_stride,
                                    bloom_word);
 }
 
@@ -244,7 +257,7 @@ LRB_DEVINL RingRec load_rec(const float4* ring, int g, bool act) {
   return r;
 }
 
-template <int STRIDE>
+template <int STRIDE, int KMAX>
 __device__ __noinline__ float compact_ring(const float4* ring, int cnt, float own_thr, float shared_thr,
                                            int row_limit_gid, uint32_t ls, uint32_t li, uint32_t ln,
                                            int K, const int* excl, uint32_t excl_s, int excl_stride,
@@ -277,7 +290,7 @@ __device__ __noinline__ float compact_ring(const float4* ring, int cnt, float ow
         const int gid = gid0 + bj;
         const int bw = (gid >> 5) & 3;
         const uint32_t bword = bw == 0 ? bloom0 : (bw == 1 ? bloom1 : (bw == 2 ? bloom2 : bloom3));
-        own_thr = topk_consider_inl<STRIDE>(best, gid, row_limit_gid, own_thr, ls, li, ln, K, excl,
+        own_thr = topk_consider_inl<STRIDE, KMAX>(best, gid, row_limit_gid, own_thr, ls, li, ln, K, excl,
                                             excl_s, excl_stride, bword);
       }
 #pragma unroll
@@ -376,7 +389,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     mbar_init(a_full_bar, 1);
     mbar_init(a_empty_bar, 1);
     mbar_fence_init();
-    sSvc[0] = -1; sSvc[1] = -1; sSvc[2] = 0;
+    sSvc[0] = -1; sSvc[1] = -1; sSvc[2] = 0; sSvc[3] = 0;
   }
   if (warp == 2) {
     tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -545,6 +558,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         sSvc[1] = seg_idx;      // the service warp starts refreshing this segment's buffer
       }
       int cnt = 0;   // records waiting in this thread's ring
+      int drain_seen = sSvc[3];   // CTA-wide drain sequence number last honoured by this warp
       bool boot = !kDense;   // warp-uniform: the first compaction of a segment happens after one chunk
       float4* ring = reinterpret_cast<float4*>(
           p.ring + (static_cast<size_t>(blockIdx.x) * EPI_THREADS + et) * (RING_GROUPS * RING_REC_BYTES));
@@ -557,7 +571,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int kk = *reinterpret_cast<volatile int*>(rowthr + r);
           if (kk != INT_MIN) shared_thr = key_to_float(kk);
         }
-        own_thr = compact_ring<EPI_THREADS>(ring, cnt, own_thr, shared_thr, limit_gid, ls, li, ln, p.K, excl,
+        own_thr = compact_ring<EPI_THREADS, KMAX>(ring, cnt, own_thr, shared_thr, limit_gid, ls, li, ln, p.K, excl,
                                             excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
         cnt = 0;
         if (live) {
@@ -582,6 +596,14 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #ifdef LRB_DEBUG_MODES
         dbg_wait += clock64() - w0;
         if (n == sg.n0 + 64) dbg_first = clock64() - dbg_t0;
+        if (p.debug_stats != nullptr && threadIdx.x == 128 && seg_idx == 0) {
+          const int k = n - sg.n0;
+          if (k <= 32 && (k & (k - 1)) == 0) {   // tiles 0,1,2,4,8,16,32
+            int slot = 0; while ((1 << slot) < k + 1 && slot < 7) ++slot;   // 0->0,1->1,2->2,4->3,8->4,16->5,32->6
+            p.debug_stats[148 * 8 + blockIdx.x * 16 + slot] = clock64() - dbg_t0;
+            p.debug_stats[148 * 8 + blockIdx.x * 16 + 8 + slot] = dbg_compact;
+          }
+        }
 #endif
 
         // rows beyond B never produce candidates: their threshold is +inf
@@ -796,7 +818,17 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // whenever some lane holds more than RING_GROUPS-8 keeps every ring within capacity.
           // The first tile of a segment always drains (bootstrap): every stream then holds K entries
           // and publishes its c-th best within the first microseconds, which defines the union bound.
-          if (__any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0))) {
+          // Drains are synchronised across the CTA's eight epilogue warps: a warp that must drain bumps a
+          // shared sequence number and every warp drains at its next tile boundary.  A drain stalls the
+          // two-deep accumulator ring for everybody, so eight simultaneous drains cost one stall, not eight.
+          const bool need = __any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0));
+          int seq = sSvc[3];
+          if (need && seq == drain_seen) {
+            if (lane == 0) atomicAdd(const_cast<int*>(&sSvc[3]), 1);
+            seq += 1;
+          }
+          if (need || seq != drain_seen) {
+            drain_seen = sSvc[3];
             boot = false;
 #ifdef LRB_DEBUG_MODES
             dbg_appends += cnt;

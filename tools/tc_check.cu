@@ -310,14 +310,14 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
     int sms = 0, cc = 0;
     lrb_device_info(&sms, &cc);
     long long* dstats;
-    CK(cudaMalloc(&dstats, sms * 8 * sizeof(long long)));
-    CK(cudaMemset(dstats, 0, sms * 8 * sizeof(long long)));
+    CK(cudaMalloc(&dstats, sms * 24 * sizeof(long long)));
+    CK(cudaMemset(dstats, 0, sms * 24 * sizeof(long long)));
     lrb_debug_set_stats(dstats);
     LK(lrb_score_topk(du, T.e16, T.bias_pad, bblk, B, rows, 0, with_excl ? dex : nullptr, with_excl ? dbl : nullptr,
                       stride, K, 0, dps, dpi, dpc, slots, scratch, nullptr));
     CK(cudaDeviceSynchronize());
     lrb_debug_set_stats(nullptr);
-    std::vector<long long> st(sms * 8);
+    std::vector<long long> st(sms * 24);
     CK(cudaMemcpy(st.data(), dstats, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     printf("  per-CTA [cycles(M) appends/thread compactions/warp tiles] for CTAs 0,1,64,127,128,137,147:\n");
     int show[7] = {0, 1, 64, 127, 128, 137, 147};
@@ -327,6 +327,11 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
       printf("   cta %3d: %.2f  %.1f  %.1f  %lld | epi-warp0: wait %.2fM compact %.2fM first64tiles %.2fM\n", c, st[c * 4] / 1e6, st[c * 4 + 1] / 256.0, st[c * 4 + 2] / 8.0, st[c * 4 + 3],
              st[sms * 4 + c * 4] / 1e6, st[sms * 4 + c * 4 + 1] / 1e6, st[sms * 4 + c * 4 + 2] / 1e6);
     }
+    printf("   cta 0 warp0 timeline (kcycles at start of tile 0,1,2,4,8,16,32 | cumulative compaction kcycles):\n    ");
+    for (int i = 0; i < 7; ++i) printf("%.0f ", st[sms * 8 + i] / 1e3);
+    printf("| ");
+    for (int i = 0; i < 7; ++i) printf("%.0f ", st[sms * 8 + 8 + i] / 1e3);
+    printf("\n");
     long long mn = 1LL << 62, mx = 0; double sum = 0;
     for (int c = 0; c < sms; ++c) { mn = std::min(mn, st[c * 4]); mx = std::max(mx, st[c * 4]); sum += st[c * 4]; }
     printf("   cycles min %.2fM max %.2fM mean %.2fM\n", mn / 1e6, mx / 1e6, sum / sms / 1e6);
