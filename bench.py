@@ -54,6 +54,8 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.index = index
+        self.t_begin = None
+        self.t_end = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -69,16 +71,29 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # samples inside the timed region; if the region is shorter than the sampling period, the
+        # samples taken under the same load just before it (warm-up) are used and flagged
+        inside = [r for (t, r) in self.rows if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t)]
+        window = "timed region"
+        if not inside:
+            inside = [r for (t, r) in self.rows if self.t_begin is None or t >= self.t_begin - 1.0]
+            window = "timed region + preceding 1 s of warm-up (region shorter than the sampling period)"
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -87,7 +102,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def model_args(n_items):
@@ -187,21 +202,34 @@ def run_product(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(ids_dev)
+    barrier()
+    # keep the GPU under the same load until the sampler has produced its first rows
+    # (the continue/stop decision is agreed between the ranks: step() contains collectives)
+    t_spin = time.time()
+    while True:
+        step(ids_dev)
+        more = torch.tensor([1 if (len(sampler.rows) < 2 and time.time() - t_spin < 2.0) else 0], device=device)
+        if world > 1:
+            dist.all_reduce(more, op=dist.ReduceOp.MAX)
+        if int(more.item()) == 0:
+            break
     barrier()
 
     # ---- device-resident timing (value) ----
     model.profile_events = []
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record()
     for _ in range(args.steps):
         out = step(ids_dev)
     ev1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     score_ms = [a.elapsed_time(b) for a, b in model.profile_events]

@@ -131,7 +131,8 @@ class LRURec(nn.Module):
     def retrieve(self, x: torch.Tensor, k: int = 20, exclude_history: bool = True,
                  labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
                  precision: str = "auto", u: Optional[torch.Tensor] = None,
-                 u_bf16: Optional[torch.Tensor] = None, merge: bool = True) -> Dict[str, torch.Tensor]:
+                 u_bf16: Optional[torch.Tensor] = None, merge: bool = True,
+                 packed_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """encode -> catalogue score -> (history mask) -> top-k -> (metrics), all on device.
 
         Replaces calculate_metrics / the per-user loop of generate_candidates (trainer/lru.py:30-42,
@@ -178,7 +179,7 @@ class LRURec(nn.Module):
             self.profile_events.append((ev0, ev1))
         if not merge:
             return {"part_scores": part_s, "part_ids": part_i, "part_cnt": part_c, "u": u}
-        out = merge_lists(part_s, part_i, part_c, k_out=k, labels=labels, ks=ks)
+        out = merge_lists(part_s, part_i, part_c, k_out=k, labels=labels, ks=ks, packed_out=packed_out)
         out["u"] = u
         return out
 
@@ -281,7 +282,8 @@ class LRURec(nn.Module):
 
 def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Optional[torch.Tensor], k_out: int,
                 labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
-                layout: str = "user_major") -> Dict[str, torch.Tensor]:
+                layout: str = "user_major", packed_out: Optional[torch.Tensor] = None,
+                strides: Optional[tuple] = None) -> Dict[str, torch.Tensor]:
     """Fused k-way merge + metrics (lrb_merge_metrics).
 
     layout 'user_major': lists are [B, S, K] (output of lrb_score_topk);
@@ -297,16 +299,24 @@ def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Opt
         S, B, K = list_scores.shape
         stride_list, stride_user = B * K, K
         cnt_sl, cnt_su = B, 1
+    if strides is not None:          # explicit element strides (views into a packed gather buffer)
+        stride_list, stride_user = strides
+    else:
+        list_scores, list_ids = list_scores.contiguous(), list_ids.contiguous()
     ks = list(ks) if ks is not None else []
-    top_s = torch.empty(B, k_out, dtype=torch.float32, device=dev)
-    top_i = torch.empty(B, k_out, dtype=torch.int32, device=dev)
+    if packed_out is not None:       # [2, B, k_out] int32: scores (bit pattern) then ids, one gather payload
+        top_s = packed_out[0].view(torch.float32)
+        top_i = packed_out[1]
+    else:
+        top_s = torch.empty(B, k_out, dtype=torch.float32, device=dev)
+        top_i = torch.empty(B, k_out, dtype=torch.int32, device=dev)
     rank = torch.empty(B, dtype=torch.int32, device=dev) if labels is not None else None
     sums = torch.zeros(max(len(ks), 1) * 3, dtype=torch.float32, device=dev) if labels is not None else None
     if labels is not None:
         labels = labels.to(dev).reshape(-1).to(torch.int64).contiguous()
     ks_arr = (_lib.ctypes.c_int32 * max(len(ks), 1))(*ks) if ks else None
     _lib.check(lib.lrb_merge_metrics(
-        _lib.ptr(list_scores.contiguous()), _lib.ptr(list_ids.contiguous()),
+        list_scores.data_ptr(), list_ids.data_ptr(),
         _lib.ptr(list_cnt.contiguous()) if list_cnt is not None else None, S, stride_list, stride_user, cnt_sl,
         cnt_su, K, B, k_out, _lib.ptr(labels), ks_arr, len(ks), _lib.ptr(top_s), _lib.ptr(top_i), _lib.ptr(rank),
         _lib.ptr(sums), _lib.stream_handle()))

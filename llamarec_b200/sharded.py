@@ -8,7 +8,7 @@ One process per GPU (`torch.distributed`, NCCL).  Per batch:
   1. every rank encodes its slice of the users (the encoder is batch-sharded: replicated encode would
      be the Amdahl term at 8 GPUs) and all-gathers the 64-d user states            [B x 64 fp32]
   2. every rank scores ALL users against ITS item rows and keeps a local top-k     (no communication)
-  3. one all-gather of the local lists                                             [R x B x k x 8 bytes]
+  3. ONE all-gather of the local lists, scores and ids packed in one payload       [R x 2 x B x k x 4 bytes]
   4. every rank merges the R lists (fused with the metrics)                        (no communication)
 
 The numerical work is delegated to a backend object so that the plumbing (ranges, padding, gather
@@ -35,6 +35,7 @@ class CudaBackend:
     def __init__(self, model, rank: int, world: int, precision: str = "auto"):
         self.model = model
         self.precision = precision
+        self._packed = {}
         lo, hi = shard_range(model.num_items + 1, rank, world)
         model.set_row_shard(lo, hi)
         self.rows = (lo, hi)
@@ -42,17 +43,30 @@ class CudaBackend:
     def encode(self, x: torch.Tensor) -> torch.Tensor:
         return self.model.encode(x)
 
-    def local_topk(self, x: torch.Tensor, u: torch.Tensor, k: int, exclude_history: bool):
-        if self.rows[1] <= self.rows[0]:   # empty shard (more ranks than 256-row tiles): nothing to offer
-            B = x.shape[0]
-            return (torch.full((B, k), float("-inf"), device=u.device), torch.full((B, k), -1, dtype=torch.int32, device=u.device))
-        res = self.model.retrieve(x, k=k, exclude_history=exclude_history, precision=self.precision, u=u)
-        return res["scores"], res["ids"]
+    def local_topk_packed(self, x: torch.Tensor, u: torch.Tensor, k: int, exclude_history: bool) -> torch.Tensor:
+        """Local top-k as ONE gather payload: int32 [2, B, k] = scores (bit pattern), ids."""
+        B = x.shape[0]
+        key = (B, k, str(u.device))
+        buf = self._packed.get(key)
+        if buf is None:
+            buf = torch.empty(2, B, k, dtype=torch.int32, device=u.device)
+            self._packed[key] = buf
+        if self.rows[1] <= self.rows[0]:   # empty shard (more ranks than rows): nothing to offer
+            buf[0].view(torch.float32).fill_(float("-inf"))
+            buf[1].fill_(-1)
+            return buf
+        self.model.retrieve(x, k=k, exclude_history=exclude_history, precision=self.precision, u=u, packed_out=buf)
+        return buf
 
-    def merge(self, list_scores, list_ids, k, labels, ks):
+    def merge_packed(self, gathered: torch.Tensor, k, labels, ks):
+        """gathered: int32 [R, 2, B, k] (all-gathered payloads) -> final lists (+ metrics)."""
         from .model import merge_lists
-        # missing entries carry id -1 / score -inf; give them count semantics through the scores
-        return merge_lists(list_scores, list_ids, None, k_out=k, labels=labels, ks=ks, layout="list_major")
+        R, _, B, K = gathered.shape
+        scores = gathered[:, 0].view(torch.float32)
+        ids = gathered[:, 1]
+        # missing entries carry id -1 / score -inf and simply never win
+        return merge_lists(scores, ids, None, k_out=k, labels=labels, ks=ks, layout="list_major",
+                           strides=(2 * B * K, K))
 
 
 class ShardedRetriever:
@@ -82,12 +96,11 @@ class ShardedRetriever:
         if hi > lo:
             u_loc[: hi - lo] = self.backend.encode(x[lo:hi])
         u = self._all_gather(u_loc).reshape(self.world * per, 64)[:B].contiguous()
-        # 2. local scoring over this rank's rows
-        s_loc, i_loc = self.backend.local_topk(x, u, k, exclude_history)
-        # 3. one all-gather of (score, id) lists
-        s_all = self._all_gather(s_loc.float().contiguous())
-        i_all = self._all_gather(i_loc.to(torch.int32).contiguous())
+        # 2. local scoring over this rank's rows -> one packed payload [2, B, k] (scores, ids)
+        payload = self.backend.local_topk_packed(x, u, k, exclude_history)
+        # 3. ONE all-gather of the (score, id) lists
+        gathered = self._all_gather(payload)
         # 4. merge (+ metrics)
-        out = self.backend.merge(s_all, i_all, k, labels, ks)
+        out = self.backend.merge_packed(gathered, k, labels, ks)
         out["u"] = u
         return out

@@ -132,7 +132,7 @@ class OracleBackend:
     def encode(self, x):
         return O.encode(x, self.sd)
 
-    def local_topk(self, x, u, k, exclude_history):
+    def local_topk_packed(self, x, u, k, exclude_history):
         s = u @ self.sd["embedding.token.weight"][self.lo:self.hi].t() + self.sd["model.bias"][self.lo:self.hi]
         if exclude_history:
             for b in range(x.shape[0]):
@@ -140,9 +140,11 @@ class OracleBackend:
                     if self.lo <= i < self.hi:
                         s[b, i - self.lo] = -1e9
         ts, ti = O.topk_sorted(s, k)
-        return ts, (ti + self.lo).to(torch.int32)
+        return torch.stack((ts.contiguous().view(torch.int32), (ti + self.lo).to(torch.int32)))
 
-    def merge(self, s_all, i_all, k, labels, ks):
+    def merge_packed(self, gathered, k, labels, ks):
+        s_all = gathered[:, 0].contiguous().view(torch.float32)
+        i_all = gathered[:, 1].contiguous()
         R, B, K = s_all.shape
         s = s_all.permute(1, 0, 2).reshape(B, R * K)
         i = i_all.permute(1, 0, 2).reshape(B, R * K).to(torch.int64)
