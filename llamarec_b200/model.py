@@ -14,6 +14,7 @@ Fast entry points added on top of the reference interface:
 from __future__ import annotations
 
 import math
+import warnings
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -65,8 +66,10 @@ class LRURec(nn.Module):
             theta_log = torch.log(u2 * (2 * math.pi))
             gamma_log = torch.log(torch.sqrt(1 - torch.exp(-torch.exp(nu_log)) ** 2))
             blk.lru_layer.params_log = nn.Parameter(torch.vstack((nu_log, theta_log, gamma_log)))
-            blk.lru_layer.in_proj = nn.Linear(d, 2 * d).to(torch.cfloat)
-            blk.lru_layer.out_proj = nn.Linear(2 * d, d).to(torch.cfloat)
+            with warnings.catch_warnings():   # torch warns that complex nn.Modules are experimental
+                warnings.simplefilter("ignore")
+                blk.lru_layer.in_proj = nn.Linear(d, 2 * d).to(torch.cfloat)
+                blk.lru_layer.out_proj = nn.Linear(2 * d, d).to(torch.cfloat)
             blk.lru_layer.layer_norm = nn.LayerNorm(d)
             blk.feed_forward = _Container()
             blk.feed_forward.w_1 = nn.Linear(d, 4 * d)

@@ -260,3 +260,59 @@ def test_full_size_10m_catalogue_properties():
         sc[0] = -1e9
         ts, ti = torch.topk(sc, K)
         assert_topk_equivalent(i[b:b + 1].numpy(), s[b:b + 1].numpy(), ti.cpu().numpy()[None], ts.cpu().numpy()[None], rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# Edge cases the reference's call sites can produce
+# ------------------------------------------------------------------------------------------------
+def test_single_user_single_position_and_int32_ids(model, golden_sd):
+    ids = torch.tensor([[7]], dtype=torch.int64)
+    res = model.retrieve(ids.cuda(), k=5, precision="fp32")
+    ref_s, ref_i = O.retrieve(ids, golden_sd, 5)
+    assert_topk_equivalent(res["ids"].cpu().numpy(), res["scores"].cpu().numpy(), ref_i.numpy(), ref_s.numpy())
+    # int32 ids are accepted (converted on device), empty history rows keep the last position
+    ids2 = torch.zeros(3, 20, dtype=torch.int32)
+    ids2[1, -3:] = torch.tensor([5, 9, 11], dtype=torch.int32)
+    res2 = model.retrieve(ids2.cuda(), k=20, precision="fp32")
+    ref_s2, ref_i2 = O.retrieve(ids2.long(), golden_sd, 20)
+    assert_topk_equivalent(res2["ids"].cpu().numpy(), res2["scores"].cpu().numpy(), ref_i2.numpy(), ref_s2.numpy())
+
+
+def test_k_larger_than_valid_items_and_no_exclusion():
+    """Tiny catalogue: 30 items, histories cover most of it, k=20 > #valid items for some users."""
+    n = 30
+    sd = synth.make_state_dict(n, seed=5, bias_std=0.05)
+    m = LRURec(_args(n))
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    rng = np.random.default_rng(0)
+    ids = np.zeros((6, 25), dtype=np.int64)
+    for b in range(6):
+        hist = rng.permutation(np.arange(1, n + 1))[: 8 + 3 * b]
+        ids[b, 25 - len(hist):] = hist
+    x = torch.from_numpy(ids)
+    for prec in ("fp32", "bf16"):
+        res = m.retrieve(x.cuda(), k=20, exclude_history=True, precision=prec)
+        got_i, got_s = res["ids"].cpu().numpy(), res["scores"].cpu().numpy()
+        for b in range(6):
+            valid = sorted(set(range(1, n + 1)) - set(ids[b].tolist()))
+            k_valid = min(20, len(valid))
+            assert set(got_i[b, :k_valid].tolist()) <= set(valid)
+            assert len(set(got_i[b, :k_valid].tolist())) == k_valid          # every valid item at most once
+            if k_valid < 20:                                                  # the rest is marked missing
+                assert np.all(got_i[b, k_valid:] == -1) and np.all(np.isinf(got_s[b, k_valid:]))
+    # exclude_history=False (BaseTrainer.validate): item 0 and history items compete (trainer/base.py:141)
+    res = m.retrieve(x.cuda(), k=10, exclude_history=False, precision="fp32")
+    ref_s, ref_i = O.retrieve(x, sd, 10, exclude_history=False)
+    assert_topk_equivalent(res["ids"].cpu().numpy(), res["scores"].cpu().numpy(), ref_i.numpy(), ref_s.numpy())
+
+
+def test_errors_are_loud():
+    from llamarec_b200._lib import LrbError
+    m = LRURec(_args(50)).cuda().eval()
+    with pytest.raises(LrbError):
+        m.retrieve(torch.ones(2, 300, dtype=torch.int64).cuda(), k=5)        # L > LRB_MAX_LEN
+    with pytest.raises(LrbError):
+        m.retrieve(torch.ones(2, 10, dtype=torch.int64).cuda(), k=64)        # K > LRB_MAX_K
+    with pytest.raises(ValueError):
+        LRURec(SimpleNamespace(num_items=10, bert_hidden_units=32, bert_num_blocks=2))
