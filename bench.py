@@ -154,14 +154,22 @@ def run_reference(args, rank, world):
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     table, bias = synth.make_table_bf16(N_ITEMS, seed=42, device=dev)
     table, bias = table.cpu(), bias.cpu()
+    # bounded sample: size the per-step user count so that warm-up + K steps take about two minutes
+    probe_users = 32
+    t_probe = cpu_oracle_run(sd, table, bias, ids, probe_users)
+    budget_s = 120.0
+    n_steps = args.warmup + args.steps
+    users = int(probe_users * (budget_s / n_steps) / max(t_probe, 1e-3))
+    users = max(8, min(CPU_SAMPLE_USERS, users))
     times = []
-    for s in range(args.warmup + args.steps):
-        dt = cpu_oracle_run(sd, table, bias, ids, CPU_SAMPLE_USERS)
+    for s in range(n_steps):
+        dt = cpu_oracle_run(sd, table, bias, ids, users)
         if s >= args.warmup:
             times.append(dt)
     total = sum(times)
-    value = CPU_SAMPLE_USERS * len(times) / total
-    sample = f"{CPU_SAMPLE_USERS} of the {BATCH} users per step against the full 10M-item table (fp32, chunked 65536 items)"
+    value = users * len(times) / total
+    sample = (f"{users} of the {BATCH} users per step against the full 10M-item table "
+              f"(fp32, chunked 65536 items, running top-20; sample sized for a ~2 min run)")
     line = {
         "impl": "reference", "metric": "users_per_sec_encode_score_top20", "value": value, "unit": "users/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),

@@ -250,11 +250,14 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const tc::ScoreParam
 
 #ifdef LRB_DEBUG_MODES
 static int g_debug_mode = 0;
+static int g_debug_scout = -1;
 static long long* g_debug_stats = nullptr;
+extern "C" void lrb_debug_set_scout(int t) { g_debug_scout = t; }
 extern "C" void lrb_debug_set_score_mode(int m) { g_debug_mode = m; }
 extern "C" void lrb_debug_set_stats(long long* p) { g_debug_stats = p; }
 #else
 static const int g_debug_mode = 0;
+static const int g_debug_scout = -1;
 static long long* const g_debug_stats = nullptr;
 #endif
 
@@ -345,6 +348,10 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     // entries each of the 2*s_full full-stream threads of a user must hold for the union bound
     const int c = d.s_full > 0 ? (K + 2 * d.s_full - 1) / (2 * d.s_full) : 99;
     p.c_share = c <= 4 ? c : 0;
+    // scout pass: worth its T0 extra tiles when the union bound exists and segments are long enough
+    const long long seg_tiles = d.s_full > 0 ? d.full_tiles / d.s_full : 0;
+    p.scout_tiles = (p.c_share > 0 && seg_tiles >= 128) ? 16 : 0;
+    if (g_debug_scout >= 0) p.scout_tiles = (p.c_share > 0) ? g_debug_scout : 0;
   }
   p.part_scores = part_scores; p.part_ids = part_ids; p.part_cnt = part_cnt; p.slots = d.slots;
   p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
@@ -395,7 +402,7 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
   p.B = static_cast<int>(M); p.m_tiles = d.m_tiles; p.rows = static_cast<int>(rows); p.n_tiles = d.n_tiles;
   p.row_offset = 0; p.K = 1; p.bias_blk = static_cast<const uint8_t*>(bias_blk);
   p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
-  p.gslots = nullptr; p.c_share = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
+  p.gslots = nullptr; p.c_share = 0; p.scout_tiles = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
   p.dense_out = out; p.dense_ld = ld_out; p.debug_mode = 0; p.debug_stats = nullptr;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
   return launch_tc<20, 3, true>(ta, tb, p, d.grid, st);

@@ -52,6 +52,8 @@ struct ScoreParams {
                                // valid lower bound on the user's K-th best (union bound), also used by the
                                // shared-stream CTAs, whose own slots are ignored (they may start late).
   int c_share;                 // c (1..4); 0 disables the union bound
+  int scout_tiles;             // T0: the last T0 tiles of every segment are first run in "scout" mode (no
+                               // candidate handling, only group maxima) to seed the union bound; 0 = off
   uint8_t* ring;               // [gridDim.x][EPI_THREADS][RING_GROUPS][RING_REC_BYTES] candidate rings
   float* part_scores;          // [B][slots][K]
   int* part_ids;               // [B][slots][K]
@@ -427,7 +429,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (seg_idx > 0) mbar_wait(a_empty_bar, (seg_idx - 1) & 1);
         mbar_expect_tx(a_full_bar, A_BYTES);
         tma_load_2d(sA, &tmap_a, a_full_bar, 0, sg.m * BM);
-        for (int n = sg.n0; n < sg.n1; ++n) {
+        const int n_scout = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
+        for (int it = -n_scout; it < sg.n1 - sg.n0; ++it) {
+          const int n = it < 0 ? sg.n1 + it : sg.n0 + it;   // scout pass re-visits the segment's last tiles
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], stage_tx);
           uint8_t* st = sB + stage * L::kStage;
@@ -453,7 +457,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint64_t desc_ones = umma_desc_k16_nosw(smem_u32(sOnes));
       while (walk.next(sg)) {
         mbar_wait(a_full_bar, seg_idx & 1);
-        for (int n = sg.n0; n < sg.n1; ++n) {
+        const int n_scout = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
+        for (int it = -n_scout; it < sg.n1 - sg.n0; ++it) {
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -559,7 +564,79 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       int cnt = 0;   // records waiting in this thread's ring
       int drain_seen = sSvc[3];   // CTA-wide drain sequence number last honoured by this warp
-      bool boot = !kDense;   // warp-uniform: the first compaction of a segment happens after one chunk
+      bool boot = !kDense;   // warp-uniform: without a scout pass the first tile of a segment always drains
+
+      // ---------------- scout pass ----------------
+      // The segment's last T0 tiles are scored once without any candidate handling: each thread only keeps
+      // the m largest 16-item group maxima it sees (m = c + E, E = excluded ids inside the scouted id range,
+      // so at least c of them belong to admissible items) and publishes the m-th.  The union bound is
+      // therefore defined before the normal pass starts, which spares it the threshold-less first tiles.
+      const int n_scout = (kDense || p.scout_tiles <= 0 || p.c_share <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
+      const int n_scout_run = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
+      if (n_scout_run > 0) {
+        float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;   // descending
+        for (int it = 0; it < n_scout_run; ++it) {
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN + half * (BN / 2));
+          uint32_t w[2][32];
+          tmem_ld_32x32(taddr, w[0]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < 3) tmem_ld_32x32(taddr + (c + 1) * 32, w[(c + 1) & 1]);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float q[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(w[c & 1][g * 16 + j]);
+              const float m1 = max3(q[0], q[1], q[2]);
+              const float m2 = max3(q[3], q[4], q[5]);
+              const float m3 = max3(q[6], q[7], q[8]);
+              const float m4 = max3(q[9], q[10], q[11]);
+              const float m5 = max3(q[12], q[13], q[14]);
+              float x = fmaxf(max3(m1, m2, m3), max3(m4, m5, q[15]));
+              float hi;
+              hi = fmaxf(t0, x); x = fminf(t0, x); t0 = hi;
+              hi = fmaxf(t1, x); x = fminf(t1, x); t1 = hi;
+              hi = fmaxf(t2, x); x = fminf(t2, x); t2 = hi;
+              t3 = fmaxf(t3, x);
+            }
+            if (c < 3) tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+        if (live && publishes && n_scout > 0) {
+          // E = excluded ids that fall inside the scouted id range (either column half)
+          int E = 0;
+          if (excl != nullptr) {
+            const int g_lo = p.row_offset + (sg.n1 - n_scout_run) * BN;
+            const int g_hi = p.row_offset + sg.n1 * BN;
+            int lo = 0, hi = p.excl_stride;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(excl + mid) < g_lo) lo = mid + 1; else hi = mid; }
+            int lo2 = lo, hi2 = p.excl_stride;
+            while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (__ldg(excl + mid) < g_hi) lo2 = mid + 1; else hi2 = mid; }
+            E = lo2 - lo;
+          }
+          const int mth = p.c_share + E;   // 1-based rank of the group maximum that is safe to publish
+          const float cb = mth == 1 ? t0 : (mth == 2 ? t1 : (mth == 3 ? t2 : (mth == 4 ? t3 : -INFINITY)));
+          if (cb > -INFINITY) {
+            published = float_to_key(cb);
+            p.gslots[static_cast<size_t>(b) * p.slots + my_slot] = published;
+          }
+        }
+        boot = false;
+        // give the threshold service a bounded moment to pick the bound up (never blocks on other CTAs)
+        for (int spin = 0; spin < 40; ++spin) {
+          const int kk = *reinterpret_cast<volatile int*>(rowthr + r);
+          if (__all_sync(0xffffffffu, kk != INT_MIN || !live)) break;
+          __nanosleep(250);
+        }
+      }
       float4* ring = reinterpret_cast<float4*>(
           p.ring + (static_cast<size_t>(blockIdx.x) * EPI_THREADS + et) * (RING_GROUPS * RING_REC_BYTES));
       const int limit_gid = p.row_offset + p.rows;

@@ -8,8 +8,11 @@
 //              normalize : softmax over all label words (post_log_softmax only)           :588-600
 //              log(p + 1e-15), aggregate = masked mean over the words of a class          :582,611-614
 //
-// HBM-bound skinny GEMM: 8 users per CTA (one warp each); the C*W label rows are staged through
-// shared memory in K-chunks of 512 so each row is read once per CTA, not once per user.
+// HBM/latency-bound skinny GEMM.  UB = 4 users per CTA: their hidden rows are staged once in shared
+// memory (32 KB at H = 4096); each of the 8 warps owns a subset of the label words and streams those
+// lm_head rows straight from L2 with 16-byte loads (a whole row's loads are issued before the first
+// FMA so ~H/256 requests per lane are in flight), dotting them with the 4 staged rows at once.  The
+// per-user post-processing (project / softmax / log / aggregate) then runs in one warp per user.
 #include "api_util.h"
 #include "common.cuh"
 
@@ -17,8 +20,9 @@ namespace lrb {
 namespace verb {
 
 constexpr int WARPS = 8;
-constexpr int KC = 512;        // K chunk (bf16 elements)
-constexpr int MAX_WORDS = 32;  // C * W upper bound
+constexpr int UB = 4;           // users per CTA
+constexpr int MAX_WORDS = 32;   // C * W upper bound
+constexpr int MAX_VEC = 32;     // 16-byte vectors per lane per row => H <= 8192
 
 struct Params {
   const __nv_bfloat16* hidden;   // [B][H]
@@ -40,69 +44,59 @@ LRB_DEVINL void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
   }
 }
 
+template <int NVEC>   // NVEC = H / 256: 16-byte vectors per lane per row
 __global__ void __launch_bounds__(WARPS * 32) verbalizer_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint4* sW = reinterpret_cast<uint4*>(smem_raw);   // [n_words][KC/8] 16-byte vectors
-  __shared__ float s_logit[WARPS][MAX_WORDS];
+  uint4* sH = reinterpret_cast<uint4*>(smem_raw);        // [UB][H/8] 16-byte vectors
+  __shared__ float s_logit[UB][MAX_WORDS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * WARPS + warp;
+  const int b0 = blockIdx.x * UB;
   const int n_words = p.C * p.W;
-  const bool live = b < p.B;
+  const int hv = p.H / 8;                                 // vectors per row
 
-  float acc[MAX_WORDS];
-#pragma unroll
-  for (int w = 0; w < MAX_WORDS; ++w) acc[w] = 0.f;
-
-  for (int k0 = 0; k0 < p.H; k0 += KC) {
-    __syncthreads();
-    // stage the label rows' chunk
-    for (int e = threadIdx.x; e < n_words * (KC / 8); e += WARPS * 32) {
-      const int w = e / (KC / 8);
-      const int v = e - w * (KC / 8);
-      long long tok = p.word_ids[w];
-      if (tok < 0 || tok >= p.V) tok = 0;
-      sW[e] = __ldg(reinterpret_cast<const uint4*>(p.lm_head + static_cast<size_t>(tok) * p.H + k0) + v);
-    }
-    // this user's chunk of the hidden state: two 16-byte vectors per lane
-    float h0[8], h1[8];
-    {
-      uint4 a = make_uint4(0u, 0u, 0u, 0u), c = a;
-      if (live) {
-        const uint4* hp = reinterpret_cast<const uint4*>(p.hidden + static_cast<size_t>(b) * p.H + k0);
-        a = __ldg(hp + lane);
-        c = __ldg(hp + 32 + lane);
-      }
-      bf16x8_to_f32(a, h0);
-      bf16x8_to_f32(c, h1);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < MAX_WORDS; ++w) {
-      if (w < n_words) {
-        float f0[8], f1[8];
-        bf16x8_to_f32(sW[w * (KC / 8) + lane], f0);
-        bf16x8_to_f32(sW[w * (KC / 8) + 32 + lane], f1);
-        float s = acc[w];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(h0[i], f0[i], s);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(h1[i], f1[i], s);
-        acc[w] = s;
-      }
-    }
+  for (int e = threadIdx.x; e < UB * hv; e += WARPS * 32) {
+    const int u = e / hv, v = e - u * hv;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (b0 + u < p.B) val = __ldg(reinterpret_cast<const uint4*>(p.hidden + static_cast<size_t>(b0 + u) * p.H) + v);
+    sH[e] = val;
   }
+  __syncthreads();
+
+  for (int w = warp; w < n_words; w += WARPS) {
+    long long tok = p.word_ids[w];
+    if (tok < 0 || tok >= p.V) tok = 0;
+    const uint4* row = reinterpret_cast<const uint4*>(p.lm_head + static_cast<size_t>(tok) * p.H);
+    uint4 wv[NVEC];
 #pragma unroll
-  for (int w = 0; w < MAX_WORDS; ++w) {
-    if (w < n_words) {
-      float s = warp_sum(acc[w]);
+    for (int j = 0; j < NVEC; ++j) wv[j] = __ldg(row + j * 32 + lane);   // all loads in flight
+    float acc[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) acc[u] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      float wf[8];
+      bf16x8_to_f32(wv[j], wf);
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        float hf[8];
+        bf16x8_to_f32(sH[u * hv + j * 32 + lane], hf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[u] = fmaf(hf[i], wf[i], acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      float s = warp_sum(acc[u]);
       if (p.round_bf16) s = __bfloat162float(__float2bfloat16_rn(s));
-      if (lane == 0) s_logit[warp][w] = s;
+      if (lane == 0) s_logit[u][w] = s;
     }
   }
-  __syncwarp();
-  if (!live) return;
+  __syncthreads();
+  if (warp >= UB) return;
+  const int b = b0 + warp;
+  if (b >= p.B) return;
 
-  // ---- verbalizer post-processing, lanes = label words ----
+  // ---- verbalizer post-processing, one warp per user, lanes = label words ----
   float x = -INFINITY;
   float m = 0.f;
   if (lane < n_words) {
@@ -119,14 +113,12 @@ __global__ void __launch_bounds__(WARPS * 32) verbalizer_kernel(const Params p) 
     x = logf(e / den + 1e-15f);
   }
   // aggregate: masked mean over the W words of each class                   (trainer/verb.py:611-614)
-  float num = lane < n_words ? x * m : 0.f;
-  float cntm = m;
-  // words of class c sit in lanes c*W .. c*W+W-1: segmented sum by walking the W neighbours
+  const float num = lane < n_words ? x * m : 0.f;
   float tot = 0.f, totm = 0.f;
   for (int j = 0; j < p.W; ++j) {
     const int src = (lane / p.W) * p.W + j;
     tot += __shfl_sync(0xffffffffu, num, src & 31);
-    totm += __shfl_sync(0xffffffffu, cntm, src & 31);
+    totm += __shfl_sync(0xffffffffu, m, src & 31);
   }
   if (lane < n_words && (lane % p.W) == 0) p.out[static_cast<size_t>(b) * p.C + lane / p.W] = tot / totm;
 }
@@ -143,8 +135,8 @@ extern "C" int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head
   LRB_REQUIRE(hidden_bf16 && lm_head_bf16 && word_ids && word_mask && out, "lrb_verbalizer_score: null pointer");
   LRB_REQUIRE(B > 0 && V > 0 && C > 0 && W > 0, "lrb_verbalizer_score: bad shape");
   LRB_REQUIRE(mode == 0 || mode == 1, "lrb_verbalizer_score: mode must be 0 (raw) or 1 (log-softmax)");
-  if (H % verb::KC != 0)
-    return set_error(LRB_ERR_UNSUPPORTED, "hidden size %d must be a multiple of %d", H, verb::KC);
+  if (H % 256 != 0 || H / 256 > verb::MAX_VEC)
+    return set_error(LRB_ERR_UNSUPPORTED, "hidden size %d must be a multiple of 256 and <= %d", H, 256 * verb::MAX_VEC);
   if (C * W > verb::MAX_WORDS)
     return set_error(LRB_ERR_UNSUPPORTED, "at most %d label words in total (got %d x %d)", verb::MAX_WORDS, C, W);
   verb::Params p;
@@ -152,9 +144,27 @@ extern "C" int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head
   p.lm_head = static_cast<const __nv_bfloat16*>(lm_head_bf16);
   p.B = B; p.H = H; p.V = V; p.word_ids = word_ids; p.word_mask = word_mask;
   p.C = C; p.W = W; p.mode = mode; p.round_bf16 = round_bf16; p.out = out;
-  const size_t smem = static_cast<size_t>(C) * W * verb::KC * 2;
-  const int grid = (B + verb::WARPS - 1) / verb::WARPS;
-  verb::verbalizer_kernel<<<grid, verb::WARPS * 32, smem, as_stream(stream)>>>(p);
+  const size_t smem = static_cast<size_t>(verb::UB) * H * 2;
+  const int grid = (B + verb::UB - 1) / verb::UB;
+  const int nvec = H / 256;
+  cudaStream_t st = as_stream(stream);
+#define LRB_VERB_LAUNCH(NV)                                                                              \
+  do {                                                                                                   \
+    LRB_CUDA_TRY(cudaFuncSetAttribute(verb::verbalizer_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      static_cast<int>(smem)));                                          \
+    verb::verbalizer_kernel<NV><<<grid, verb::WARPS * 32, smem, st>>>(p);                                \
+  } while (0)
+  if (nvec <= 2) { if (nvec == 1) LRB_VERB_LAUNCH(1); else LRB_VERB_LAUNCH(2); }
+  else if (nvec <= 4) { if (nvec == 3) LRB_VERB_LAUNCH(3); else LRB_VERB_LAUNCH(4); }
+  else if (nvec == 6) LRB_VERB_LAUNCH(6);
+  else if (nvec == 8) LRB_VERB_LAUNCH(8);
+  else if (nvec == 12) LRB_VERB_LAUNCH(12);
+  else if (nvec == 14) LRB_VERB_LAUNCH(14);
+  else if (nvec == 16) LRB_VERB_LAUNCH(16);
+  else if (nvec == 20) LRB_VERB_LAUNCH(20);
+  else if (nvec == 32) LRB_VERB_LAUNCH(32);
+  else return set_error(LRB_ERR_UNSUPPORTED, "hidden size %d is not one of the instantiated widths", H);
+#undef LRB_VERB_LAUNCH
   LRB_CUDA_TRY(cudaGetLastError());
   return LRB_OK;
 }
