@@ -63,7 +63,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -210,8 +210,10 @@ def run_product(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one sampler (rank 0's GPU) is enough and keeps driver polling away from the other ranks
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(ids_dev)
     barrier()
@@ -220,7 +222,8 @@ def run_product(args, rank, world, local_rank):
     t_spin = time.time()
     while True:
         step(ids_dev)
-        more = torch.tensor([1 if (len(sampler.rows) < 2 and time.time() - t_spin < 2.0) else 0], device=device)
+        waiting = rank == 0 and sampler.proc is not None and len(sampler.rows) < 2 and time.time() - t_spin < 2.0
+        more = torch.tensor([1 if waiting else 0], device=device)
         if world > 1:
             dist.all_reduce(more, op=dist.ReduceOp.MAX)
         if int(more.item()) == 0:

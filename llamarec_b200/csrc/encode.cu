@@ -113,10 +113,10 @@ LRB_DEVINL void copy_weights(float* dst, const float* __restrict__ src, int n_fl
 }
 
 // LayerNorm over 64 features of `rows` rows held in Cs[row][65]; one warp per row at a time.
-// Two-pass (mean, then centred variance) like torch's CPU kernel.  Result goes to dst_t (k-major
-// At layout, may be null) and/or dst_g (global row-major [row][64], may be null).
-LRB_DEVINL void layernorm_rows(const float* Cs, int n_rows, const float* __restrict__ w,
-                               const float* __restrict__ b, float* dst_t, float* dst_g_base,
+// Two-pass (mean, then centred variance) like torch's CPU kernel.  The result replaces the row in
+// Cs (row-major, conflict-free) and optionally goes to global memory (row-major [row][64]).
+LRB_DEVINL void layernorm_rows(float* Cs, int n_rows, const float* __restrict__ w,
+                               const float* __restrict__ b, float* dst_g_base,
                                const int* s_dst_row, int warp, int lane) {
   const float w0 = __ldg(w + lane), w1 = __ldg(w + lane + 32);
   const float b0 = __ldg(b + lane), b1 = __ldg(b + lane + 32);
@@ -128,10 +128,8 @@ LRB_DEVINL void layernorm_rows(const float* Cs, int n_rows, const float* __restr
     const float rstd = 1.0f / sqrtf(var + LN_EPS);
     const float o0 = d0 * rstd * w0 + b0;
     const float o1 = d1 * rstd * w1 + b1;
-    if (dst_t != nullptr) {
-      dst_t[lane * TOK + r] = o0;
-      dst_t[(lane + 32) * TOK + r] = o1;
-    }
+    Cs[r * 65 + lane] = o0;
+    Cs[r * 65 + lane + 32] = o1;
     if (dst_g_base != nullptr) {
       const int row = s_dst_row[r];
       if (row >= 0) {
@@ -139,6 +137,14 @@ LRB_DEVINL void layernorm_rows(const float* Cs, int n_rows, const float* __restr
         dst_g_base[static_cast<size_t>(row) * D + lane + 32] = o1;
       }
     }
+  }
+}
+
+// Row-major Cs[row][65] -> k-major At[k][TOK]; lanes walk the rows, so both sides are conflict-free.
+LRB_DEVINL void transpose_rows_to_kmajor(const float* Cs, float* At, int tid) {
+  for (int e = tid; e < TOK * D; e += THREADS) {
+    const int r = e & (TOK - 1), k = e / TOK;
+    At[k * TOK + r] = Cs[r * 65 + k];
   }
 }
 
@@ -197,12 +203,14 @@ __global__ void __launch_bounds__(THREADS, 1) embed_inproj_kernel(const InprojPa
         if (lane == 0) s_row[r] = i < T ? i : -1;
       }
       __syncthreads();
-      layernorm_rows(Cs, TOK, p.wts + OFF_EMB_LN_W, p.wts + OFF_EMB_LN_B, At, p.x0_out, s_row, warp, lane);
+      layernorm_rows(Cs, TOK, p.wts + OFF_EMB_LN_W, p.wts + OFF_EMB_LN_B, p.x0_out, s_row, warp, lane);
+      __syncthreads();
+      transpose_rows_to_kmajor(Cs, At, tid);
     } else {
-      // load x tile (row-major [i][64]) transposed into At
+      // load x tile (row-major [i][64]) transposed into At; lanes walk the rows (conflict-free stores)
       for (int e = tid; e < TOK * D / 4; e += THREADS) {
-        const int r = e / (D / 4);
-        const int k4 = e - r * (D / 4);
+        const int r = e & (TOK - 1);
+        const int k4 = e / TOK;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i0 + r < T) v = *reinterpret_cast<const float4*>(p.x_in + static_cast<size_t>(i0 + r) * D + k4 * 4);
         At[(k4 * 4 + 0) * TOK + r] = v.x;
@@ -354,8 +362,8 @@ __global__ void __launch_bounds__(THREADS, 1) outproj_ffn_kernel(const OutParams
     __syncthreads();
     // ---- stage h (transposed), the residual rows, W_out ----
     for (int e = tid; e < TOK * H2 / 4; e += THREADS) {
-      const int r = e / (H2 / 4);
-      const int k4 = e - r * (H2 / 4);
+      const int r = e & (TOK - 1);      // lanes walk the rows: conflict-free transposed stores
+      const int k4 = e / TOK;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i0 + r < n_rows_total) v = *reinterpret_cast<const float4*>(p.h + static_cast<size_t>(i0 + r) * H2 + k4 * 4);
       Ht[(k4 * 4 + 0) * TOK + r] = v.x;
@@ -394,14 +402,17 @@ __global__ void __launch_bounds__(THREADS, 1) outproj_ffn_kernel(const OutParams
       }
     }
     __syncthreads();
-    // LN -> Yt (k-major, GEMM input).  The row-major copy for the PFFN residual is written below.
-    layernorm_rows(Cs, TOK, blkw + B_LN1_W, blkw + B_LN1_B, Yt, nullptr, s_row, warp, lane);
+    // LN in place (row-major y, also the PFFN residual), then a conflict-free transpose into Yt
+    layernorm_rows(Cs, TOK, blkw + B_LN1_W, blkw + B_LN1_B, nullptr, s_row, warp, lane);
     copy_weights(Ws, blkw + B_W1_T, D * FF, tid);   // W_out no longer needed (all GEMM reads done)
     __syncthreads();
     for (int e = tid; e < TOK * D; e += THREADS) {
-      const int r = e & 63, k = e >> 6;
-      Ys[r * 65 + k] = Yt[k * TOK + r];
+      const int r = e & (TOK - 1), k = e / TOK;
+      const float yv = Cs[r * 65 + k];
+      Yt[k * TOK + r] = yv;
+      Ys[r * 65 + k] = yv;
     }
+    __syncthreads();
     {
       // ---- f = gelu_erf(y W1^T + b1) -> Ht (k-major [256][TOK]) ----
       const int ty8 = tid >> 5, tx8 = tid & 31;
@@ -445,23 +456,14 @@ __global__ void __launch_bounds__(THREADS, 1) outproj_ffn_kernel(const OutParams
       }
     }
     __syncthreads();
-    layernorm_rows(Cs, TOK, blkw + B_LN2_W, blkw + B_LN2_B, nullptr, p.x_out, s_row, warp, lane);
+    layernorm_rows(Cs, TOK, blkw + B_LN2_W, blkw + B_LN2_B, p.x_out, s_row, warp, lane);
     if (p.out_bf16 != nullptr) {
-      __syncthreads();   // not strictly needed for correctness of Cs; LN wrote only to global
-      // bf16 copy recomputed from the fp32 rows just written by this CTA's own threads is avoided:
-      // redo the normalisation cheaply per row instead of re-reading global memory.
-      const float w0 = __ldg(blkw + B_LN2_W + lane), w1 = __ldg(blkw + B_LN2_W + lane + 32);
-      const float c0 = __ldg(blkw + B_LN2_B + lane), c1 = __ldg(blkw + B_LN2_B + lane + 32);
+      // bf16 copy of the rows this warp just normalised in place (same warp -> same rows, no barrier)
       for (int r = warp; r < TOK; r += THREADS / 32) {
         const int rowi = s_row[r];
         if (rowi < 0) continue;
-        const float v0 = Cs[r * 65 + lane], v1 = Cs[r * 65 + lane + 32];
-        const float mean = warp_sum(v0 + v1) * (1.0f / 64.0f);
-        const float d0 = v0 - mean, d1 = v1 - mean;
-        const float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / 64.0f);
-        const float rstd = 1.0f / sqrtf(var + LN_EPS);
-        p.out_bf16[static_cast<size_t>(rowi) * D + lane] = __float2bfloat16_rn(d0 * rstd * w0 + c0);
-        p.out_bf16[static_cast<size_t>(rowi) * D + lane + 32] = __float2bfloat16_rn(d1 * rstd * w1 + c1);
+        p.out_bf16[static_cast<size_t>(rowi) * D + lane] = __float2bfloat16_rn(Cs[r * 65 + lane]);
+        p.out_bf16[static_cast<size_t>(rowi) * D + lane + 32] = __float2bfloat16_rn(Cs[r * 65 + lane + 32]);
       }
     }
   }

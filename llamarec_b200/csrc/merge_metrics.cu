@@ -99,15 +99,42 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
     float prev_s = INFINITY;
     int prev_id = -1;
     for (int k = 0; k < p.K_out; ++k) {
-      float bs = -INFINITY;
-      int bi = INT_MAX;
-      int bq = -1;
+      float w_s;
+      int w_id;
       if (in_regs) {
+        // lane-local best score (max tree), warp-wide maximum by one redux on the order-preserving key
+        float bs = es[0];
+#pragma unroll
+        for (int q = 1; q + 1 < PER_LANE; q += 2) bs = max3(bs, es[q], es[q + 1]);
+        bs = fmaxf(bs, es[PER_LANE - 1]);
+        const int key = float_to_key(bs);
+        const int wkey = __reduce_max_sync(0xffffffffu, key);
+        const bool mine = key == wkey;
+        // among this lane's entries that carry the winning score: lowest id, and how many there are
+        int bi = INT_MAX, n_eq = 0;
 #pragma unroll
         for (int q = 0; q < PER_LANE; ++q) {
-          if (better(es[q], ei[q], bs, bi)) { bs = es[q]; bi = ei[q]; bq = q; }
+          const bool eq = mine && es[q] == bs;
+          bi = (eq && ei[q] < bi) ? ei[q] : bi;
+          n_eq += eq ? 1 : 0;
+        }
+        // ties across lanes (or inside one) resolve towards the lowest id
+        w_id = __reduce_min_sync(0xffffffffu, mine ? bi : INT_MAX);
+        w_s = key_to_float(wkey);
+        if (wkey == float_to_key(-INFINITY)) { w_id = INT_MAX; w_s = -INFINITY; }
+        (void)n_eq;
+        // the owner of (w_s, w_id) retires that entry (first match only, so duplicates stay countable)
+        bool done = !(mine && bi == w_id) || w_id == INT_MAX;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; ++q) {
+          const bool hit = !done && es[q] == w_s && ei[q] == w_id;
+          es[q] = hit ? -INFINITY : es[q];
+          ei[q] = hit ? INT_MAX : ei[q];
+          done = done || hit;
         }
       } else {
+        float bs = -INFINITY;
+        int bi = INT_MAX;
         for (int e = lane; e < total_slots; e += 32) {
           const int l = e / p.K_in;
           const int i = e - l * p.K_in;
@@ -119,21 +146,18 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
           if (!(better(prev_s, prev_id, s, d))) continue;
           if (better(s, d, bs, bi)) { bs = s; bi = d; }
         }
+        const Best w = warp_best(bs, bi, lane);
+        w_s = w.s;
+        w_id = w.id;
       }
-      const Best w = warp_best(bs, bi, lane);
-      if (in_regs && w.lane == lane && bq >= 0) {
-#pragma unroll
-        for (int q = 0; q < PER_LANE; ++q)
-          if (q == bq) { es[q] = -INFINITY; ei[q] = INT_MAX; }
-      }
-      prev_s = w.s;
-      prev_id = w.id;
-      const bool valid = w.id != INT_MAX;
+      prev_s = w_s;
+      prev_id = w_id;
+      const bool valid = w_id != INT_MAX;
       if (lane == 0) {
-        p.top_scores[static_cast<size_t>(b) * p.K_out + k] = valid ? w.s : -INFINITY;
-        p.top_ids[static_cast<size_t>(b) * p.K_out + k] = valid ? w.id : -1;
+        p.top_scores[static_cast<size_t>(b) * p.K_out + k] = valid ? w_s : -INFINITY;
+        p.top_ids[static_cast<size_t>(b) * p.K_out + k] = valid ? w_id : -1;
       }
-      if (valid && my_rank < 0 && static_cast<long long>(w.id) == label) my_rank = k;
+      if (valid && my_rank < 0 && static_cast<long long>(w_id) == label) my_rank = k;
     }
     if (p.label_rank && lane == 0) p.label_rank[b] = my_rank;
     if (p.labels && my_rank >= 0 && lane == 0) {
