@@ -5,10 +5,13 @@ on the scaled synthetic catalogue (configs[3]: 10M items, d=64, batch 4096, L=50
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch of 4096 synthetic users: sequence preparation,
+One "step" = one pass of the hot path over one batch of 4096 synthetic users per GPU: sequence preparation,
 encoder, catalogue scoring fused with top-20, k-way merge + metrics.  With N > 1 the item table is
-row-sharded over the ranks (strong scaling: the batch and the catalogue are fixed), the encoder is
-batch-sharded, and two all-gathers (user states, local top-20 lists) connect them.
+row-sharded over the ranks and the users are data-parallel (weak scaling: every rank brings its own batch
+of 4096 users, the global batch is 4096*N, per-GPU scoring work is constant): one coalesced all-gather of
+the user states + exclusion lists, local scoring of all 4096*N users against the rank's rows, one
+all-to-all of the local top-20 lists, merge of the local users' N lists.  `--scaling strong` instead keeps
+the global batch at 4096 (every rank scores the same 4096 users against 1/N of the rows).
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference's path on the
 host cores instead (the reference is pure Python/PyTorch; /root/reference is not on the GPU box).
@@ -110,9 +113,9 @@ def model_args(n_items):
                            bert_attn_dropout=0.2)
 
 
-def make_inputs():
+def make_inputs(seed=42):
     from llamarec_b200 import synth
-    return synth.make_sequences_fast(BATCH, N_ITEMS, MAX_LEN, seed=42)
+    return synth.make_sequences_fast(BATCH, N_ITEMS, MAX_LEN, seed=seed)
 
 
 def build_product_model(device):
@@ -173,7 +176,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "users_per_sec_encode_score_top20", "value": value, "unit": "users/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "max_len": MAX_LEN, "k": TOPK},
         "cpu_baseline": {"value": value, "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -189,7 +192,8 @@ def run_product(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     model, sd = build_product_model(device)
-    ids_host, labels_host = make_inputs()
+    weak = world > 1 and args.scaling == "weak"
+    ids_host, labels_host = make_inputs(42 + rank if weak else 42)     # weak: every rank has its own users
     ids_pinned = ids_host.pin_memory()
     ids_dev = ids_host.to(device)
     labels_dev = labels_host.to(device)
@@ -197,7 +201,8 @@ def run_product(args, rank, world, local_rank):
 
     if world > 1:
         retr = ShardedRetriever(CudaBackend(model, rank, world, precision="bf16"))
-        step = lambda x: retr.retrieve(x, k=TOPK, exclude_history=True, labels=labels_dev, ks=ks)
+        fn = retr.retrieve_dp if weak else retr.retrieve
+        step = lambda x: fn(x, k=TOPK, exclude_history=True, labels=labels_dev, ks=ks)
         rows = shard_range(N_ITEMS + 1, rank, world)
         local_rows = rows[1] - rows[0]
     else:
@@ -276,9 +281,12 @@ def run_product(args, rank, world, local_rank):
         return
     pk = peaks()
     ms_per_step = ms_total / args.steps
-    value = BATCH * args.steps / (ms_total * 1e-3)
-    e2e_value = BATCH * args.steps / e2e_s
-    flops = 2.0 * BATCH * local_rows * 64                       # algorithmic FLOPs of one scoring launch
+    global_batch = BATCH * world if weak else BATCH
+    value = global_batch * args.steps / (ms_total * 1e-3)
+    e2e_value = global_batch * args.steps / e2e_s
+    flops = 2.0 * global_batch * local_rows * 64                # algorithmic FLOPs of one rank's scoring call
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    score_launches = -(-global_batch // (128 * sms))            # one launch per chunk of 128 x SMs users
     achieved = flops / (score_ms_mean * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -290,15 +298,21 @@ def run_product(args, rank, world, local_rank):
     line = {
         "metric": "users_per_sec_encode_score_top20", "value": value, "unit": "users/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "max_len": MAX_LEN, "k": TOPK,
-                   "parallelism": f"row-sharded item table x{world}, batch-sharded encoder" if world > 1 else "single GPU",
+        "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "batch_per_gpu": BATCH if (weak or world == 1) else BATCH // world,
+                   "global_batch": global_batch, "max_len": MAX_LEN, "k": TOPK,
+                   "parallelism": (f"item table row-sharded x{world}; users data-parallel ({BATCH} per GPU); all-gather of "
+                                   f"user states, all-to-all of local top-{TOPK} lists" if weak else
+                                   f"item table row-sharded x{world}, same {BATCH} users on every rank, batch-sharded encoder"
+                                   if world > 1 else "single GPU"),
                    "l2": "item table (1.28 GB bf16) is 10x larger than L2; no flush needed",
                    "scoring_operands": "bf16 table and user state, fp32 accumulate (tcgen05); encoder fp32"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": ids_pinned.numel() * 8,
-                "d2h_bytes_per_step": BATCH * TOPK * 8 + len(ks) * 3 * 4},
-        "gpu_launches": args.steps * (2 + 6 + 1 + 1 + (1 if world > 1 else 0)),
+        "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": ids_pinned.numel() * 8 * (world if weak else 1),
+                "d2h_bytes_per_step": (BATCH * TOPK * 8 + len(ks) * 3 * 4) * (world if weak else 1)},
+        # per step: prepare_sequences, 6 encoder kernels, scoring launch(es), local merge (+ final merge)
+        "gpu_launches": args.steps * (1 + 6 + score_launches + 1 + (1 if world > 1 else 0)),
         "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": achieved,
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
@@ -324,6 +338,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 4096 users per GPU (default), strong = 4096 users in total")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling convenience: omit the ~20 s CPU oracle leg (the default run includes it)")
     args = ap.parse_args()

@@ -141,7 +141,9 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
  *          [B][slots][K] layout of lrb_score_topk and the [R][B][K] layout after an all-gather.
  *   labels [B] int64 (NULL = no metrics)     ks [n_ks] host array, ascending or not
  * Outputs
- *   top_scores/top_ids [B][K_out]  sorted by (score desc, id asc); missing entries = (-inf, -1)
+ *   top_scores/top_ids [B][K_out]  sorted by (score desc, id asc); missing entries = (-inf, -1);
+ *                consecutive users are out_stride elements apart (0 = K_out, i.e. dense), so both
+ *                arrays can live interleaved in one exchange payload [B][2][K_out]
  *   label_rank [B] int32: 0-based rank of the label in the merged list, -1 if absent
  *   metric_sums [3*n_ks] fp32: per k (in the order given) sum over users of Recall, MRR, NDCG
  *                (accumulated: the caller zeroes it once per epoch / per batch as it prefers)
@@ -150,7 +152,7 @@ int lrb_merge_metrics(const float* list_scores, const int32_t* list_ids, const i
                       int n_lists, int64_t stride_list, int64_t stride_user, int64_t cnt_stride_list,
                       int64_t cnt_stride_user, int K_in, int B, int K_out, const int64_t* labels,
                       const int32_t* ks_host, int n_ks, float* top_scores, int32_t* top_ids,
-                      int32_t* label_rank, float* metric_sums, void* stream);
+                      int64_t out_stride, int32_t* label_rank, float* metric_sums, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stage-2 verbalizer tail.  Replaces lm_head on the last position (model/llm.py:113-114,131) and

@@ -35,7 +35,7 @@ SIGNATURES = {
                                 c_void_p]),
     "lrb_merge_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
                                   c_int, c_int, c_void_p, POINTER(ctypes.c_int32), c_int, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p]),
+                                  c_int64, c_void_p, c_void_p, c_void_p]),
     "lrb_verbalizer_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_void_p, c_void_p]),
 }

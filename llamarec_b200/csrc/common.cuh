@@ -189,6 +189,77 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // ----------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one tcgen05.mma spans both SMs of a TPC.  Each CTA
+// holds its own 128 accumulator rows and HALF of the B tile; the leader (cluster rank 0) issues the
+// MMAs, its mbarriers collect the TMA bytes of both CTAs and the "accumulator drained" arrivals of
+// both epilogues; tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs.
+// ----------------------------------------------------------------------------
+LRB_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+LRB_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+LRB_DEVINL uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+LRB_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+LRB_DEVINL void red_add_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are accounted on a barrier given as a
+// shared::cluster address (the leader's barrier).
+LRB_DEVINL void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr),
+      "r"(c0), "r"(c1)
+      : "memory");
+}
+LRB_DEVINL void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+LRB_DEVINL void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+LRB_DEVINL void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA].  Leader thread only.
+LRB_DEVINL void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at the same shared-memory offset in every CTA of `cta_mask` once all
+// previously issued tcgen05.mma of this thread retire.
+LRB_DEVINL void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------
 // Packed fp32x2 add and 3-input max (both new on sm_100).
 // ----------------------------------------------------------------------------
 LRB_DEVINL void add_f32x2(float& a0, float& a1, float b0, float b1) {

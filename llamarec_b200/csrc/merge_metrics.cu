@@ -33,8 +33,9 @@ struct Params {
   const long long* labels;     // may be null
   int ks[MAX_KS];
   int n_ks;
-  float* top_scores;           // [B][K_out]
-  int* top_ids;                // [B][K_out]
+  float* top_scores;           // [B][K_out], rows out_stride elements apart
+  int* top_ids;                // [B][K_out], rows out_stride elements apart
+  long long out_stride;
   int* label_rank;             // [B] (may be null)
   float* metric_sums;          // [3*n_ks] (may be null)
 };
@@ -154,8 +155,8 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
       prev_id = w_id;
       const bool valid = w_id != INT_MAX;
       if (lane == 0) {
-        p.top_scores[static_cast<size_t>(b) * p.K_out + k] = valid ? w_s : -INFINITY;
-        p.top_ids[static_cast<size_t>(b) * p.K_out + k] = valid ? w_id : -1;
+        p.top_scores[static_cast<size_t>(b) * p.out_stride + k] = valid ? w_s : -INFINITY;
+        p.top_ids[static_cast<size_t>(b) * p.out_stride + k] = valid ? w_id : -1;
       }
       if (valid && my_rank < 0 && static_cast<long long>(w_id) == label) my_rank = k;
     }
@@ -196,7 +197,8 @@ extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_i
                                  int n_lists, int64_t stride_list, int64_t stride_user,
                                  int64_t cnt_stride_list, int64_t cnt_stride_user, int K_in, int B, int K_out,
                                  const int64_t* labels, const int32_t* ks_host, int n_ks, float* top_scores,
-                                 int32_t* top_ids, int32_t* label_rank, float* metric_sums, void* stream) {
+                                 int32_t* top_ids, int64_t out_stride, int32_t* label_rank, float* metric_sums,
+                                 void* stream) {
   using namespace lrb;
   int rc = check_arch();
   if (rc != LRB_OK) return rc;
@@ -204,6 +206,7 @@ extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_i
   LRB_REQUIRE(n_lists >= 1 && K_in >= 1 && B >= 1 && K_out >= 1, "lrb_merge_metrics: bad shape");
   LRB_REQUIRE(n_ks >= 0 && n_ks <= mm::MAX_KS, "lrb_merge_metrics: at most %d cut-offs", mm::MAX_KS);
   LRB_REQUIRE(n_ks == 0 || ks_host != nullptr, "lrb_merge_metrics: ks missing");
+  LRB_REQUIRE(out_stride == 0 || out_stride >= K_out, "lrb_merge_metrics: out_stride must be 0 or >= K_out");
   mm::Params p;
   p.list_scores = list_scores; p.list_ids = list_ids; p.list_cnt = list_cnt; p.n_lists = n_lists;
   p.stride_list = stride_list; p.stride_user = stride_user;
@@ -213,6 +216,7 @@ extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_i
   for (int i = 0; i < mm::MAX_KS; ++i) p.ks[i] = i < n_ks ? ks_host[i] : 0;
   p.n_ks = labels ? n_ks : 0;
   p.top_scores = top_scores; p.top_ids = top_ids; p.label_rank = label_rank;
+  p.out_stride = out_stride > 0 ? out_stride : K_out;
   p.metric_sums = (labels && n_ks > 0) ? metric_sums : nullptr;
   const int grid = (B + mm::WARPS - 1) / mm::WARPS;
   mm::merge_metrics_kernel<<<grid, mm::WARPS * 32, 0, as_stream(stream)>>>(p);

@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 namespace lrb {
 
@@ -170,9 +171,12 @@ struct Decomp {
   int m_tiles, n_tiles, s_full, rem, full_tiles, y_tiles, grid, slots;
 };
 
-Decomp decompose(int B, long long rows, int sms) {
+// `units` = independent MMA engines (SMs, or SM pairs when two CTAs share one tcgen05.mma), `bm` = users
+// per engine tile (128 per CTA).
+Decomp decompose(int B, long long rows, int units, int bm = tc::BM) {
+  const int sms = units;
   Decomp d;
-  d.m_tiles = (B + tc::BM - 1) / tc::BM;
+  d.m_tiles = (B + bm - 1) / bm;
   d.n_tiles = static_cast<int>((rows + tc::BN - 1) / tc::BN);
   long long work = static_cast<long long>(d.m_tiles) * d.n_tiles;
   int G = static_cast<int>(work < sms ? work : sms);
@@ -198,6 +202,37 @@ Decomp decompose(int B, long long rows, int sms) {
   d.grid = d.s_full * d.m_tiles + d.rem;
   d.slots = 2 * (d.s_full + (d.rem > 0 ? 2 : 0));
   return d;
+}
+
+// A launch covers at most one 128-user tile per SM: every CTA of a full stream then sweeps the same item
+// tiles at about the same time (one HBM read per tile, the rest L2 hits).  Larger batches (the all-gathered
+// users of a data-parallel job) are processed as consecutive launches over user chunks.
+inline int users_per_launch(int sms) { return sms * tc::BM; }
+
+// CTA pairs (tcgen05 cta_group::2) whenever a launch has more than one user tile: the pair shares every
+// item tile, which halves the shared-memory operand traffic and the L2 -> SM traffic per MMA.
+inline int cta_group_for(int B, int sms) {
+  static const int forced = [] {
+    const char* e = std::getenv("LRB_SCORE_CTA_GROUP");   // tuning knob: "1" keeps every launch on single CTAs
+    return e ? std::atoi(e) : 0;
+  }();
+  if (forced == 1) return 1;
+  return (B > tc::BM && sms >= 2) ? 2 : 1;
+}
+
+Decomp decompose_launch(int B, long long rows, int sms) {
+  const int cg = cta_group_for(B, sms);
+  return decompose(B, rows, sms / cg, tc::BM * cg);
+}
+
+int chunked_slots(int B, long long rows, int sms) {
+  const int cap = users_per_launch(sms);
+  int slots = 0;
+  for (int c0 = 0; c0 < B; c0 += cap) {
+    const int s = decompose_launch(B - c0 < cap ? B - c0 : cap, rows, sms).slots;
+    slots = s > slots ? s : slots;
+  }
+  return slots;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -234,13 +269,42 @@ int make_tmap_bf16_k64(CUtensorMap* out, const void* ptr, unsigned long long row
   return LRB_OK;
 }
 
-template <int KMAX, int NS, bool kDense>
-int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const tc::ScoreParams& p, int grid,
-              cudaStream_t st) {
-  using L = tc::SmemLayout<KMAX, NS>;
-  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense>;
+// folded-bias blocks as a [bytes/256][256] uint8 matrix: a CTA of a pair fetches its 4 KB half as a
+// 16-row box (lands contiguously; no swizzle), accounted on the leader's barrier like the item rows
+int make_tmap_bias_blocks(CUtensorMap* out, const void* ptr, unsigned long long n_tiles) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(LRB_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {256ull, n_tiles * (tc::BIASBLK_BYTES / 256)};
+  cuuint64_t strides[1] = {256ull};
+  cuuint32_t box[2] = {256u, static_cast<cuuint32_t>(tc::BIASBLK_BYTES / 2 / 256)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(LRB_ERR_DRIVER, "cuTensorMapEncodeTiled (bias blocks) failed (%d)", (int)r);
+  return LRB_OK;
+}
+
+// `grid` counts MMA engines: CTAs for CG == 1, CTA pairs (clusters of 2) for CG == 2.
+template <int KMAX, int NS, bool kDense, int CG>
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbias, const tc::ScoreParams& p,
+              int grid, cudaStream_t st) {
+  using L = tc::SmemLayout<KMAX, NS, CG>;
+  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG>;
   LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
-  kern<<<grid, tc::THREADS, L::kAlloc, st>>>(ta, tb, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid * CG));
+  cfg.blockDim = dim3(tc::THREADS);
+  cfg.dynamicSmemBytes = L::kAlloc;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG > 1 ? 1 : 0;
+  LRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbias, p));
   LRB_CUDA_TRY(cudaGetLastError());
   return LRB_OK;
 }
@@ -251,13 +315,16 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const tc::ScoreParam
 #ifdef LRB_DEBUG_MODES
 static int g_debug_mode = 0;
 static int g_debug_scout = -1;
+static int g_debug_pair_drain = 1;
 static long long* g_debug_stats = nullptr;
+extern "C" void lrb_debug_set_pair_drain(int v) { g_debug_pair_drain = v; }
 extern "C" void lrb_debug_set_scout(int t) { g_debug_scout = t; }
 extern "C" void lrb_debug_set_score_mode(int m) { g_debug_mode = m; }
 extern "C" void lrb_debug_set_stats(long long* p) { g_debug_stats = p; }
 #else
 static const int g_debug_mode = 0;
 static const int g_debug_scout = -1;
+static const int g_debug_pair_drain = 1;
 static long long* const g_debug_stats = nullptr;
 #endif
 
@@ -268,7 +335,7 @@ int lrb_score_topk_slots(int B, int64_t rows, int precision, int* slots) {
   int sms = lrb::device_sm_count();
   if (sms <= 0) sms = 148;
   if (precision == 0) {
-    *slots = lrb::decompose(B, rows, sms).slots;
+    *slots = lrb::chunked_slots(B, rows, sms);
   } else if (precision == 1) {
     *slots = lrb::f32::splits_for(B, rows, sms);
   } else {
@@ -281,9 +348,11 @@ int lrb_score_topk_slots(int B, int64_t rows, int precision, int* slots) {
 static size_t gslots_bytes(int B) {
   int sms = lrb::device_sm_count();
   if (sms <= 0) sms = 148;
-  const size_t m_tiles = (static_cast<size_t>(B) + lrb::tc::BM - 1) / lrb::tc::BM;
+  size_t m_tiles = (static_cast<size_t>(B) + lrb::tc::BM - 1) / lrb::tc::BM;
+  if (m_tiles > static_cast<size_t>(sms)) m_tiles = static_cast<size_t>(sms);   // one launch never covers more
   const size_t max_slots = 2 * (static_cast<size_t>(sms) / m_tiles + 2);
-  return (m_tiles * lrb::tc::BM * max_slots * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  // (+1 tile: CTA pairs pad the user tiles to an even count)
+  return ((m_tiles + 1) * lrb::tc::BM * max_slots * sizeof(int) + 255) & ~static_cast<size_t>(255);
 }
 
 size_t lrb_score_scratch_bytes(int B) {
@@ -330,37 +399,68 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
   }
   LRB_REQUIRE(precision == 0, "precision must be 0 (bf16) or 1 (fp32)");
   LRB_REQUIRE(scratch != nullptr, "lrb_score_topk: scratch is required for the bf16 path");
-  const Decomp d = decompose(B, rows, sms);
-  LRB_REQUIRE(slots == d.slots, "lrb_score_topk: slots=%d but lrb_score_topk_slots says %d", slots, d.slots);
-  CUtensorMap ta, tb;
-  rc = make_tmap_bf16_k64(&ta, u, static_cast<unsigned long long>(B), tc::BM);
+  const int want_slots = chunked_slots(B, rows, sms);
+  LRB_REQUIRE(slots == want_slots, "lrb_score_topk: slots=%d but lrb_score_topk_slots says %d", slots, want_slots);
+  CUtensorMap tb1, tb2, tbias;
+  rc = make_tmap_bf16_k64(&tb1, table, static_cast<unsigned long long>(rows), tc::BN);
   if (rc != LRB_OK) return rc;
-  rc = make_tmap_bf16_k64(&tb, table, static_cast<unsigned long long>(rows), tc::BN);
+  rc = make_tmap_bf16_k64(&tb2, table, static_cast<unsigned long long>(rows), tc::BN / 2);
   if (rc != LRB_OK) return rc;
-  tc::ScoreParams p;
-  p.B = B; p.m_tiles = d.m_tiles; p.rows = static_cast<int>(rows); p.n_tiles = d.n_tiles;
-  p.row_offset = static_cast<int>(row_offset); p.K = K;
-  p.bias_blk = static_cast<const uint8_t*>(bias_blk);
-  p.excl_sorted = excl_sorted; p.excl_bloom = excl_bloom; p.excl_stride = excl_stride;
-  p.gslots = static_cast<int*>(scratch);
-  p.ring = static_cast<uint8_t*>(scratch) + gslots_bytes(B);
-  {
-    // entries each of the 2*s_full full-stream threads of a user must hold for the union bound
-    const int c = d.s_full > 0 ? (K + 2 * d.s_full - 1) / (2 * d.s_full) : 99;
-    p.c_share = c <= 4 ? c : 0;
-    // scout pass: worth its T0 extra tiles when the union bound exists and segments are long enough
-    const long long seg_tiles = d.s_full > 0 ? d.full_tiles / d.s_full : 0;
-    p.scout_tiles = (p.c_share > 0 && seg_tiles >= 128) ? 16 : 0;
-    if (g_debug_scout >= 0) p.scout_tiles = (p.c_share > 0) ? g_debug_scout : 0;
+  tbias = tb1;   // placeholder when there is no bias block (never dereferenced)
+  if (bias_blk != nullptr) {
+    rc = make_tmap_bias_blocks(&tbias, bias_blk, static_cast<unsigned long long>((rows + tc::BN - 1) / tc::BN));
+    if (rc != LRB_OK) return rc;
   }
-  p.part_scores = part_scores; p.part_ids = part_ids; p.part_cnt = part_cnt; p.slots = d.slots;
-  p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
-  p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
-  LRB_CUDA_TRY(cudaMemsetAsync(part_cnt, 0, static_cast<size_t>(B) * d.slots * sizeof(int), st));
-  LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, static_cast<size_t>(d.m_tiles) * tc::BM * d.slots * sizeof(int), st));
-  if (K <= 20) return launch_tc<20, 3, false>(ta, tb, p, d.grid, st);
-  if (K <= 32) return launch_tc<32, 3, false>(ta, tb, p, d.grid, st);
-  return launch_tc<50, 2, false>(ta, tb, p, d.grid, st);
+  LRB_CUDA_TRY(cudaMemsetAsync(part_cnt, 0, static_cast<size_t>(B) * slots * sizeof(int), st));
+  const int cap = users_per_launch(sms);
+  for (int c0 = 0; c0 < B; c0 += cap) {
+    // one launch per chunk of <= 128 * SMs users (see users_per_launch); chunk-relative pointers
+    const int Bc = B - c0 < cap ? B - c0 : cap;
+    const int cg = cta_group_for(Bc, sms);
+    const Decomp d = decompose_launch(Bc, rows, sms);
+    CUtensorMap ta;
+    rc = make_tmap_bf16_k64(&ta, static_cast<const uint8_t*>(u) + static_cast<size_t>(c0) * 128,
+                            static_cast<unsigned long long>(Bc), tc::BM);
+    if (rc != LRB_OK) return rc;
+    tc::ScoreParams p;
+    p.B = Bc; p.m_tiles = d.m_tiles; p.rows = static_cast<int>(rows); p.n_tiles = d.n_tiles;
+    p.row_offset = static_cast<int>(row_offset); p.K = K;
+    p.bias_blk = static_cast<const uint8_t*>(bias_blk);
+    p.excl_sorted = excl_sorted ? excl_sorted + static_cast<size_t>(c0) * excl_stride : nullptr;
+    p.excl_bloom = excl_bloom ? excl_bloom + static_cast<size_t>(c0) * 4 : nullptr;
+    p.excl_stride = excl_stride;
+    p.gslots = static_cast<int*>(scratch);
+    p.gstride = d.slots;
+    p.pair_drain = g_debug_pair_drain;
+    p.ring = static_cast<uint8_t*>(scratch) + gslots_bytes(B);
+    {
+      // entries each of the 2*s_full full-stream threads of a user must hold for the union bound
+      const int c = d.s_full > 0 ? (K + 2 * d.s_full - 1) / (2 * d.s_full) : 99;
+      p.c_share = c <= 4 ? c : 0;
+      // scout pass: worth its T0 extra tiles when the union bound exists and segments are long enough
+      const long long seg_tiles = d.s_full > 0 ? d.full_tiles / d.s_full : 0;
+      p.scout_tiles = (p.c_share > 0 && seg_tiles >= 128) ? 16 : 0;
+      if (g_debug_scout >= 0) p.scout_tiles = (p.c_share > 0) ? g_debug_scout : 0;
+    }
+    p.part_scores = part_scores + static_cast<size_t>(c0) * slots * K;
+    p.part_ids = part_ids + static_cast<size_t>(c0) * slots * K;
+    p.part_cnt = part_cnt + static_cast<size_t>(c0) * slots;
+    p.slots = slots;
+    p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
+    p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
+    LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, static_cast<size_t>(d.m_tiles) * tc::BM * cg * d.slots * sizeof(int), st));
+    if (cg == 2) {
+      if (K <= 20) rc = launch_tc<20, 4, false, 2>(ta, tb2, tbias, p, d.grid, st);
+      else if (K <= 32) rc = launch_tc<32, 4, false, 2>(ta, tb2, tbias, p, d.grid, st);
+      else rc = launch_tc<50, 3, false, 2>(ta, tb2, tbias, p, d.grid, st);
+    } else {
+      if (K <= 20) rc = launch_tc<20, 3, false, 1>(ta, tb1, tbias, p, d.grid, st);
+      else if (K <= 32) rc = launch_tc<32, 3, false, 1>(ta, tb1, tbias, p, d.grid, st);
+      else rc = launch_tc<50, 2, false, 1>(ta, tb1, tbias, p, d.grid, st);
+    }
+    if (rc != LRB_OK) return rc;
+  }
+  return LRB_OK;
 }
 
 int lrb_score_dense(const void* x, const void* table, const float* bias_pad, const void* bias_blk,
@@ -402,10 +502,10 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
   p.B = static_cast<int>(M); p.m_tiles = d.m_tiles; p.rows = static_cast<int>(rows); p.n_tiles = d.n_tiles;
   p.row_offset = 0; p.K = 1; p.bias_blk = static_cast<const uint8_t*>(bias_blk);
   p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
-  p.gslots = nullptr; p.c_share = 0; p.scout_tiles = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
+  p.gslots = nullptr; p.gstride = 0; p.pair_drain = 0; p.c_share = 0; p.scout_tiles = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
   p.dense_out = out; p.dense_ld = ld_out; p.debug_mode = 0; p.debug_stats = nullptr;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
-  return launch_tc<20, 3, true>(ta, tb, p, d.grid, st);
+  return launch_tc<20, 3, true, 1>(ta, tb, tb, p, d.grid, st);
 }
 
 }  // extern "C"

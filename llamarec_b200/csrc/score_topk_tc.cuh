@@ -52,13 +52,15 @@ struct ScoreParams {
                                // valid lower bound on the user's K-th best (union bound), also used by the
                                // shared-stream CTAs, whose own slots are ignored (they may start late).
   int c_share;                 // c (1..4); 0 disables the union bound
+  int pair_drain;              // CTA pairs: a drain request is forwarded to the peer CTA (1) or stays local (0)
   int scout_tiles;             // T0: the last T0 tiles of every segment are first run in "scout" mode (no
                                // candidate handling, only group maxima) to seed the union bound; 0 = off
   uint8_t* ring;               // [gridDim.x][EPI_THREADS][RING_GROUPS][RING_REC_BYTES] candidate rings
   float* part_scores;          // [B][slots][K]
   int* part_ids;               // [B][slots][K]
   int* part_cnt;               // [B][slots]   (zeroed by the host wrapper)
-  int slots;
+  int slots;                   // stride (in lists) of the part_* arrays
+  int gstride;                 // stride (in ints) of gslots rows: the slot count of THIS launch
   float* dense_out;            // dense mode only: [B][dense_ld], columns < rows written
   long long dense_ld;
   int debug_mode;              // harness only (LRB_DEBUG_MODES): 2 = null epilogue, 3 = TMEM loads only
@@ -306,10 +308,14 @@ constexpr int EX_CAP = 56;   // ints per row of the shared-memory exclusion copy
 constexpr int BIASBLK_BYTES = BN * 16 * 2;   // one tile of the folded-bias K=16 block (8 KB)
 constexpr int ONES_BYTES = BM * 16 * 2;      // the matching [128][16] "ones" A block (4 KB)
 
-template <int KMAX, int NS>
+// CG = CTAs per MMA (tcgen05 cta_group): with CG == 2 every CTA stages only its half of the item tile
+// (128 rows) and of the bias block; the pair's MMA reads both halves.
+template <int KMAX, int NS, int CG = 1>
 struct SmemLayout {
   static constexpr bool kExclSmem = (KMAX <= 20);   // larger K variants have no room for it
-  static constexpr int kStage = B_BYTES + BIASBLK_BYTES;   // item tile + its bias block
+  static constexpr int kBBytes = B_BYTES / CG;              // this CTA's part of the item tile
+  static constexpr int kBiasBytes = BIASBLK_BYTES / CG;     // ... and of the folded-bias block
+  static constexpr int kStage = kBBytes + kBiasBytes;
   static constexpr int kA = 0;
   static constexpr int kOnes = kA + A_BYTES;
   static constexpr int kB = kOnes + ONES_BYTES;            // 20 KB offset: 1024-aligned
@@ -340,11 +346,17 @@ LRB_DEVINL uint64_t umma_desc_k16_nosw(uint32_t smem_addr) {
   return d;                                     // layout type 0 = no swizzle
 }
 
-template <int KMAX, int NS, bool kDense>
+template <int KMAX, int NS, bool kDense, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                     const __grid_constant__ CUtensorMap tmap_b, const ScoreParams p) {
-  using L = SmemLayout<KMAX, NS>;
+                     const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_bias, const ScoreParams p) {
+  using L = SmemLayout<KMAX, NS, CG>;
+  static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
+  // CTA pair: cluster rank 0 leads (issues the MMAs, owns the barriers the pair synchronises on);
+  // the pair walks the segments of "pair index" blockIdx.x / 2 and CTA `rank` owns user tile 2*m + rank.
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int walk_id = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -386,7 +398,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], EPI_WARPS);
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS * CG);   // pair: both CTAs' epilogues arrive on the leader's
     }
     mbar_init(a_full_bar, 1);
     mbar_init(a_empty_bar, 1);
@@ -394,8 +406,13 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     sSvc[0] = -1; sSvc[1] = -1; sSvc[2] = 0; sSvc[3] = 0;
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_s, TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(tmem_ptr_s, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_s, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   if (warp == 3) {
     // "ones" block: column 0..2 = 1.0 (they multiply the hi/mid/lo bf16 terms of the bias)
@@ -412,33 +429,60 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything remote arrives
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      SegmentWalk walk(p, blockIdx.x);
+      SegmentWalk walk(p, walk_id);
       Segment sg;
       int stage = 0;
       uint32_t phase = 0;
       int seg_idx = 0;
-      const uint32_t stage_tx = B_BYTES + (has_bias ? BIASBLK_BYTES : 0);
+      // bytes the (leader's) full barrier expects per stage: the parts of both CTAs
+      const uint32_t stage_tx = (L::kBBytes + (has_bias ? L::kBiasBytes : 0)) * CG;
+      const uint32_t a_full_lead = CG == 2 ? mapa_u32(smem_u32(a_full_bar), 0) : 0u;
       while (walk.next(sg)) {
+        const int m_own = CG == 2 ? sg.m * 2 + static_cast<int>(cta_rank) : sg.m;
         if (seg_idx > 0) mbar_wait(a_empty_bar, (seg_idx - 1) & 1);
-        mbar_expect_tx(a_full_bar, A_BYTES);
-        tma_load_2d(sA, &tmap_a, a_full_bar, 0, sg.m * BM);
+        if (CG == 2) {
+          if (cta_rank == 0) mbar_expect_tx(a_full_bar, A_BYTES * 2);
+          tma_load_2d_pair(sA, &tmap_a, a_full_lead, 0, m_own * BM);
+        } else {
+          mbar_expect_tx(a_full_bar, A_BYTES);
+          tma_load_2d(sA, &tmap_a, a_full_bar, 0, m_own * BM);
+        }
         const int n_scout = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
         for (int it = -n_scout; it < sg.n1 - sg.n0; ++it) {
           const int n = it < 0 ? sg.n1 + it : sg.n0 + it;   // scout pass re-visits the segment's last tiles
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], stage_tx);
+#ifdef LRB_DEBUG_MODES
+          if ((p.debug_mode == 60 || p.debug_mode == 62 || p.debug_mode == 64) && ++dbg_tiles > NS) {
+            mbar_arrive(&full_bar[stage]);   // probe: reuse the resident stage, no TMA traffic
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+            continue;
+          }
+#endif
           uint8_t* st = sB + stage * L::kStage;
-          tma_load_2d(st, &tmap_b, &full_bar[stage], 0, n * BN);
-          if (has_bias)
-            bulk_load_1d(st + B_BYTES, p.bias_blk + static_cast<size_t>(n) * BIASBLK_BYTES,
-                         BIASBLK_BYTES, &full_bar[stage]);
+          if (CG == 2) {
+            // each CTA fetches its 128 item rows (and its half of the bias block); all bytes are
+            // accounted on the leader's barrier, which alone gates the pair's MMA
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+            const uint32_t full_lead = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(st, &tmap_b, full_lead, 0, n * BN + static_cast<int>(cta_rank) * (BN / 2));
+            if (has_bias)
+              tma_load_2d_pair(st + L::kBBytes, &tmap_bias, full_lead, 0,
+                               n * (BIASBLK_BYTES / 256) + static_cast<int>(cta_rank) * (L::kBiasBytes / 256));
+          } else {
+            mbar_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_2d(st, &tmap_b, &full_bar[stage], 0, n * BN);
+            if (has_bias)
+              bulk_load_1d(st + B_BYTES, p.bias_blk + static_cast<size_t>(n) * BIASBLK_BYTES,
+                           BIASBLK_BYTES, &full_bar[stage]);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
         ++seg_idx;
@@ -446,9 +490,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      SegmentWalk walk(p, blockIdx.x);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+      SegmentWalk walk(p, walk_id);
       Segment sg;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -465,19 +509,32 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t st = smem_u32(sB + stage * L::kStage);
           const uint64_t desc_b0 = umma_desc_k_sw128(st);
           const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * BN);
+#ifdef LRB_DEBUG_MODES
+          if (p.debug_mode != 63 && p.debug_mode != 64)   // probes 63/64: no MMA
+#endif
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 32 bytes (16 bf16) along K inside the 128-B swizzle atom: +2 in 16-B units
-            umma_bf16_ss(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_ss_pair(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+            else umma_bf16_ss(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
           }
           // folded bias: D += ones[128x16] * bias_blk[256x16]^T  (hi + mid + lo bf16 terms)
-          if (has_bias) umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_nosw(st + B_BYTES), idesc, 1u);
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&tmem_full_bar[acc]);
+          if (has_bias) {
+            if (CG == 2) umma_bf16_ss_pair(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
+            else umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
+          }
+          if (CG == 2) {
+            umma_commit_pair(&empty_bar[stage], 0b11);
+            umma_commit_pair(&tmem_full_bar[acc], 0b11);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            umma_commit(&tmem_full_bar[acc]);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1; }
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(a_empty_bar);
+        if (CG == 2) umma_commit_pair(a_empty_bar, 0b11);
+        else umma_commit(a_empty_bar);
         ++seg_idx;
       }
     }
@@ -495,7 +552,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int rr = lane; rr < BM; rr += 32) {
             const int b = m * BM + rr;
             if (b >= p.B) continue;
-            const volatile int* gs = p.gslots + static_cast<size_t>(b) * p.slots;
+            const volatile int* gs = p.gslots + static_cast<size_t>(b) * p.gstride;
             int mn = INT_MAX;
             for (int sl = 0; sl < 2 * p.s_full; ++sl) {
               const int v = gs[sl];
@@ -518,14 +575,26 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t li = smem_u32(sListI + et);
     const uint32_t ln = smem_u32(sListN + et);
 
-    SegmentWalk walk(p, blockIdx.x);
+    SegmentWalk walk(p, walk_id);
     Segment sg;
     int acc = 0;
     uint32_t acc_phase = 0;
     int seg_idx = -1;
+    // "accumulator stage drained": local barrier, or the leader's for a CTA pair
+    uint32_t acc_empty_addr[ACC_STAGES];
+#pragma unroll
+    for (int i = 0; i < ACC_STAGES; ++i)
+      acc_empty_addr[i] = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[i]), 0) : smem_u32(&tmem_empty_bar[i]);
+    auto release_acc = [&](int a) {
+      if (CG == 2) mbar_arrive_cluster(acc_empty_addr[a]);
+      else mbar_arrive(&tmem_empty_bar[a]);
+    };
+    const uint32_t peer_drain_addr =
+        CG == 2 ? mapa_u32(smem_u32(const_cast<int*>(&sSvc[3])), cta_rank ^ 1u) : 0u;
     while (walk.next(sg)) {
       ++seg_idx;
-      const int b = sg.m * BM + r;
+      const int m_own = CG == 2 ? sg.m * 2 + static_cast<int>(cta_rank) : sg.m;
+      const int b = m_own * BM + r;
       const bool live = b < p.B;
       int* rowthr = sRowThr + (seg_idx & 1) * BM;
       // per-segment state reset
@@ -550,7 +619,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int i = et; i < total; i += EPI_THREADS) {
           const int rr = i / p.excl_stride;
           const int cc = i - rr * p.excl_stride;
-          const int bb = sg.m * BM + rr;
+          const int bb = m_own * BM + rr;
           sExcl[rr * EX_CAP + cc] =
               bb < p.B ? p.excl_sorted[static_cast<size_t>(bb) * p.excl_stride + cc] : INT_MAX;
         }
@@ -558,7 +627,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // threshold buffer reset / sExcl visible
       if (et == 0) {
-        sSvc[0] = sg.m;
+        sSvc[0] = m_own;
         __threadfence_block();
         sSvc[1] = seg_idx;      // the service warp starts refreshing this segment's buffer
       }
@@ -607,7 +676,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc(acc);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
         if (live && publishes && n_scout > 0) {
@@ -626,7 +695,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const float cb = mth == 1 ? t0 : (mth == 2 ? t1 : (mth == 3 ? t2 : (mth == 4 ? t3 : -INFINITY)));
           if (cb > -INFINITY) {
             published = float_to_key(cb);
-            p.gslots[static_cast<size_t>(b) * p.slots + my_slot] = published;
+            p.gslots[static_cast<size_t>(b) * p.gstride + my_slot] = published;
           }
         }
         boot = false;
@@ -658,7 +727,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const int key = float_to_key(cb);
             if (cb > -INFINITY && key > published) {
               published = key;
-              p.gslots[static_cast<size_t>(b) * p.slots + my_slot] = key;   // monotone, single writer
+              p.gslots[static_cast<size_t>(b) * p.gstride + my_slot] = key;   // monotone, single writer
             }
           }
         }
@@ -702,7 +771,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc(acc);
           int hits = 0;
           const int nrep = p.debug_mode == 52 ? 2 : (p.debug_mode == 53 ? 4 : 1);
           for (int rep = 0; rep < nrep; ++rep)
@@ -731,7 +800,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
           continue;
         }
-        if (p.debug_mode >= 20) {
+        if (p.debug_mode >= 20 && p.debug_mode < 50) {
           // 5 repetitions of the tile's four x32 loads with 1 (mode 20), 4 (mode 30) loads in flight,
           // or eight x16 loads with 2 in flight (mode 40)
           uint32_t acc_x = 0;
@@ -759,11 +828,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (acc_x == 0x12345678u) p.gslots[0] = 1;
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc(acc);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
           continue;
         }
-        if (p.debug_mode >= 10) {
+        if (p.debug_mode >= 10 && p.debug_mode < 20) {
           // repeat the four x32 loads (debug_mode - 9) times per tile: measures TMEM->RF bandwidth
           const int reps = p.debug_mode - 9;
           uint32_t acc_x = 0;
@@ -783,7 +852,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (acc_x == 0x12345678u) p.gslots[0] = 1;
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc(acc);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
           continue;
         }
@@ -801,12 +870,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (acc_x == 0x12345678u) p.gslots[0] = 1;
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc(acc);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
           continue;
         }
-        if (p.debug_mode == 2 || p.debug_mode == 3) {
-          if (p.debug_mode == 3) {
+        if (p.debug_mode == 2 || p.debug_mode == 3 || (p.debug_mode >= 60 && p.debug_mode <= 64)) {
+          if (p.debug_mode == 3 || p.debug_mode == 62) {
             uint32_t w[32];
             uint32_t acc_x = 0;
 #pragma unroll
@@ -820,7 +889,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc(acc);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
           continue;
         }
@@ -835,7 +904,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[c & 1][j]);
           if (kDense) {
-            const int row = sg.m * BM + r;
+            const int row = m_own * BM + r;
             const int col0 = n * BN + half * (BN / 2) + c * 32;
             if (row < p.B) {
               float* dst = p.dense_out + static_cast<size_t>(row) * p.dense_ld + col0;
@@ -887,7 +956,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // hand the stage back to the MMA warp before chewing on the last chunk.
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) release_acc(acc);
           }
         }
         if (!kDense) {
@@ -901,7 +970,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const bool need = __any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0));
           int seq = sSvc[3];
           if (need && seq == drain_seen) {
-            if (lane == 0) atomicAdd(const_cast<int*>(&sSvc[3]), 1);
+            if (lane == 0) {
+              atomicAdd(const_cast<int*>(&sSvc[3]), 1);
+              // a drain stalls the pair's accumulator ring: let the peer CTA drain at the same time
+              if (CG == 2 && p.pair_drain) red_add_cluster_u32(peer_drain_addr, 1u);
+            }
             seq += 1;
           }
           if (need || seq != drain_seen) {
@@ -952,10 +1025,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 #endif
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's tile halves / arrive on its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 #ifdef LRB_DEBUG_MODES
   if (p.debug_stats != nullptr && threadIdx.x == 0) p.debug_stats[blockIdx.x * 4] = clock64() - dbg_t0;

@@ -135,7 +135,7 @@ class LRURec(nn.Module):
                  labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
                  precision: str = "auto", u: Optional[torch.Tensor] = None,
                  u_bf16: Optional[torch.Tensor] = None, merge: bool = True,
-                 packed_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                 packed_out: Optional[torch.Tensor] = None, seq: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """encode -> catalogue score -> (history mask) -> top-k -> (metrics), all on device.
 
         Replaces calculate_metrics / the per-user loop of generate_candidates (trainer/lru.py:30-42,
@@ -144,16 +144,27 @@ class LRURec(nn.Module):
         per-batch sums of Recall/MRR/NDCG@ks (divide by the user count of your choice: per batch for
         BaseTrainer.validate/test, num_users for generate_candidates -- SURVEY section 8a).
         With merge=False the per-split partial lists are returned instead (used by the sharded path).
+        `seq` (optional) is a prepared descriptor holding `excl_sorted`/`excl_bloom`/`excl_stride` for the
+        rows of `u`; with it `x` may be None -- the sharded path scores user states and exclusion lists
+        that were encoded on other ranks.
         """
         lib = _lib.load()
         c = self._prepare()
         dev = c["table_f32"].device
-        x = x.to(dev).contiguous()
-        B, L = x.shape
         rows = self.row_end - self.row_begin
         prec = self._precision(precision, rows)
-        seq = self._prepare_sequences(x, all_positions=False, want_excl=exclude_history)
-        if u is None:
+        if x is None:
+            if seq is None or (u is None and u_bf16 is None):
+                raise ValueError("retrieve(x=None) needs the user states (u / u_bf16) and a prepared `seq`")
+            B = (u if u is not None else u_bf16).shape[0]
+        else:
+            x = x.to(dev).contiguous()
+            B = x.shape[0]
+            if seq is None:
+                seq = self._prepare_sequences(x, all_positions=False, want_excl=exclude_history)
+        if u is None and u_bf16 is not None and prec == 0:
+            pass                                    # bf16 states supplied by the caller
+        elif u is None:
             u, u_bf16, _ = self._encode(x, all_positions=False, want_bf16=(prec == 0), seq=seq)
         elif prec == 0 and u_bf16 is None:
             u_bf16 = u.to(torch.bfloat16).contiguous()
@@ -307,9 +318,17 @@ def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Opt
     else:
         list_scores, list_ids = list_scores.contiguous(), list_ids.contiguous()
     ks = list(ks) if ks is not None else []
-    if packed_out is not None:       # [2, B, k_out] int32: scores (bit pattern) then ids, one gather payload
+    out_stride = 0
+    if packed_out is not None and packed_out.shape[0] == 2 and packed_out.dim() == 3 and packed_out.shape[1] == B:
+        # [2, B, k_out] int32: scores (bit pattern) then ids, one gather payload
         top_s = packed_out[0].view(torch.float32)
         top_i = packed_out[1]
+    elif packed_out is not None:
+        # [B, 2, k_out] int32: per user scores then ids (rows of an all-to-all payload split by user range)
+        assert tuple(packed_out.shape) == (B, 2, k_out) and packed_out.is_contiguous()
+        top_s = packed_out.view(torch.float32)[:, 0]
+        top_i = packed_out[:, 1]
+        out_stride = 2 * k_out
     else:
         top_s = torch.empty(B, k_out, dtype=torch.float32, device=dev)
         top_i = torch.empty(B, k_out, dtype=torch.int32, device=dev)
@@ -321,8 +340,8 @@ def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Opt
     _lib.check(lib.lrb_merge_metrics(
         list_scores.data_ptr(), list_ids.data_ptr(),
         _lib.ptr(list_cnt.contiguous()) if list_cnt is not None else None, S, stride_list, stride_user, cnt_sl,
-        cnt_su, K, B, k_out, _lib.ptr(labels), ks_arr, len(ks), _lib.ptr(top_s), _lib.ptr(top_i), _lib.ptr(rank),
-        _lib.ptr(sums), _lib.stream_handle()))
+        cnt_su, K, B, k_out, _lib.ptr(labels), ks_arr, len(ks), top_s.data_ptr(), top_i.data_ptr(), out_stride,
+        _lib.ptr(rank), _lib.ptr(sums), _lib.stream_handle()))
     out = {"scores": top_s, "ids": top_i}
     if labels is not None:
         out["label_rank"] = rank

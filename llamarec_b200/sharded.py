@@ -11,6 +11,15 @@ One process per GPU (`torch.distributed`, NCCL).  Per batch:
   3. ONE all-gather of the local lists, scores and ids packed in one payload       [R x 2 x B x k x 4 bytes]
   4. every rank merges the R lists (fused with the metrics)                        (no communication)
 
+Two batch layouts are supported:
+  * `retrieve(x)`     -- every rank passes the SAME batch (strong scaling: fixed batch, fixed catalogue);
+  * `retrieve_dp(x)`  -- every rank passes ITS OWN batch of b users (data-parallel users x row-sharded items,
+                         weak scaling: the global batch is R*b).  Per step:
+      1. encode the local users; ONE coalesced all-gather of (user state, exclusion list, filter)
+      2. score all R*b users against the local item rows, local top-k              (no communication)
+      3. ONE all-to-all: the lists of rank j's users go to rank j                   [R x b x 2 x k x 4 bytes]
+      4. merge the R lists of the local users (fused with the metrics)             (no communication)
+
 The numerical work is delegated to a backend object so that the plumbing (ranges, padding, gather
 layout) can be exercised on CPU with gloo in tests; the product backend drives the CUDA kernels.
 """
@@ -58,6 +67,46 @@ class CudaBackend:
         self.model.retrieve(x, k=k, exclude_history=exclude_history, precision=self.precision, u=u, packed_out=buf)
         return buf
 
+    # ---- data-parallel users (retrieve_dp) ----
+    def encode_states(self, x: torch.Tensor, exclude_history: bool):
+        """Local users -> what the other ranks need to score them: user state [b, 64] (bf16 for the tensor-core
+        path, fp32 for the exact path), sorted exclusion list [b, stride] and its filter [b, 4]."""
+        m = self.model
+        rows = m.row_end - m.row_begin
+        prec = m._precision(self.precision, max(rows, 1))
+        x = x.to(m.embedding.token.weight.device).contiguous()
+        seq = m._prepare_sequences(x, all_positions=False, want_excl=exclude_history)
+        u, u16, _ = m._encode(x, all_positions=False, want_bf16=(prec == 0), seq=seq)
+        return {"state": u16 if prec == 0 else u, "excl": seq["excl_sorted"], "bloom": seq["excl_bloom"],
+                "excl_stride": seq["excl_stride"], "u": u}
+
+    def local_topk_rows(self, state: torch.Tensor, excl, bloom, excl_stride: int, k: int) -> torch.Tensor:
+        """All R*b users against this rank's rows -> int32 [R*b, 2, k]: per user scores (bit pattern), ids."""
+        B = state.shape[0]
+        key = ("rows", B, k, str(state.device))
+        buf = self._packed.get(key)
+        if buf is None:
+            buf = torch.empty(B, 2, k, dtype=torch.int32, device=state.device)
+            self._packed[key] = buf
+        if self.rows[1] <= self.rows[0]:
+            buf.view(torch.float32)[:, 0].fill_(float("-inf"))
+            buf[:, 1].fill_(-1)
+            return buf
+        seq = {"excl_sorted": excl, "excl_bloom": bloom, "excl_stride": excl_stride}
+        kw = {"u_bf16": state} if state.dtype == torch.bfloat16 else {"u": state}
+        self.model.retrieve(None, k=k, exclude_history=excl is not None, precision=self.precision, seq=seq,
+                            packed_out=buf, **kw)
+        return buf
+
+    def merge_rows(self, recv: torch.Tensor, k, labels, ks):
+        """recv: int32 [R, b, 2, k] (row j = rank j's lists for the local users) -> final lists (+ metrics)."""
+        from .model import merge_lists
+        R, b, _, K = recv.shape
+        scores = recv.view(torch.float32)[:, :, 0]
+        ids = recv[:, :, 1]
+        return merge_lists(scores, ids, None, k_out=k, labels=labels, ks=ks, layout="list_major",
+                           strides=(b * 2 * K, 2 * K))
+
     def merge_packed(self, gathered: torch.Tensor, k, labels, ks):
         """gathered: int32 [R, 2, B, k] (all-gathered payloads) -> final lists (+ metrics)."""
         from .model import merge_lists
@@ -75,6 +124,8 @@ class ShardedRetriever:
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._bufs = {}
+        self._coalesce = dist.is_initialized() and dist.get_backend(group) == "nccl"
 
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -83,6 +134,57 @@ class ShardedRetriever:
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t, group=self.group)   # concatenated along dim 0 (gloo and nccl)
         return out.reshape((self.world,) + tuple(t.shape))
+
+    def _all_gather_many(self, tensors):
+        """All-gathers several per-rank tensors (None entries pass through) as ONE collective launch where the
+        backend can coalesce them (NCCL group), else one after the other.  Outputs are [R*b, ...]."""
+        if self.world == 1:
+            return list(tensors)
+        outs = []
+        for i, t in enumerate(tensors):
+            if t is None:
+                outs.append(None)
+                continue
+            key = ("ag", i, tuple(t.shape), t.dtype, str(t.device))
+            o = self._bufs.get(key)
+            if o is None:
+                o = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                self._bufs[key] = o
+            outs.append(o)
+        pairs = [(o, t.contiguous()) for o, t in zip(outs, tensors) if t is not None]
+        if self._coalesce and len(pairs) > 1:
+            try:
+                with dist._coalescing_manager(group=self.group, device=pairs[0][1].device, async_ops=False):
+                    for o, t in pairs:
+                        dist.all_gather_into_tensor(o, t, group=self.group)
+                return outs
+            except (RuntimeError, NotImplementedError, AttributeError, TypeError):
+                self._coalesce = False       # backend without coalescing support: plain calls from now on
+        for o, t in pairs:
+            dist.all_gather_into_tensor(o, t, group=self.group)
+        return outs
+
+    @torch.no_grad()
+    def retrieve_dp(self, x: torch.Tensor, k: int = 20, exclude_history: bool = True,
+                    labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None) -> Dict[str, torch.Tensor]:
+        """x: THIS rank's users [b, L] (every rank passes the same b; labels likewise [b]).  Returns the final
+        top-k of the local users against the WHOLE catalogue (+ metric sums over the local users)."""
+        b = x.shape[0]
+        st = self.backend.encode_states(x, exclude_history)
+        state, excl, bloom = self._all_gather_many([st["state"], st["excl"], st["bloom"]])
+        payload = self.backend.local_topk_rows(state, excl, bloom, st["excl_stride"], k)      # [R*b, 2, k]
+        if self.world > 1:
+            key = ("a2a", tuple(payload.shape), str(payload.device))
+            recv = self._bufs.get(key)
+            if recv is None:
+                recv = torch.empty_like(payload)
+                self._bufs[key] = recv
+            dist.all_to_all_single(recv, payload, group=self.group)
+        else:
+            recv = payload
+        out = self.backend.merge_rows(recv.view(self.world, b, 2, k), k, labels, ks)
+        out["u"] = st["u"]
+        return out
 
     @torch.no_grad()
     def retrieve(self, x: torch.Tensor, k: int = 20, exclude_history: bool = True,

@@ -33,6 +33,13 @@ assert torch.equal(out["ids"], ref["ids"]), "sharded ids differ"
 assert torch.equal(out["scores"], ref["scores"]), "sharded scores differ"
 assert torch.equal(out["label_rank"], ref["label_rank"])
 assert torch.allclose(out["metric_sums"], ref["metric_sums"], rtol=1e-5)
+# data-parallel users: each rank brings its own slice, gets its own users' lists against the whole catalogue
+b = 384
+lo = rank * b
+dp = sh.retrieve_dp(ids[lo:lo + b].cuda(), k=20, labels=labels[lo:lo + b].cuda(), ks=[1, 5, 10, 20])
+assert torch.equal(dp["ids"], ref["ids"][lo:lo + b]), "dp ids differ"
+assert torch.equal(dp["scores"], ref["scores"][lo:lo + b]), "dp scores differ"
+assert torch.equal(dp["label_rank"], ref["label_rank"][lo:lo + b])
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -227,6 +227,47 @@ def test_virtual_rank_sharding_is_exact(games_model):
         assert torch.equal(merged["ids"], full["ids"]) and torch.equal(merged["scores"], full["scores"])
 
 
+def test_batches_beyond_one_tile_per_sm_are_chunked(games_model):
+    """More users than 128 x SMs (the all-gathered users of a data-parallel job): scored as consecutive launches
+    over user chunks; every user's list equals what a small-batch call returns for the same user."""
+    m, sd, cfg = games_model
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 128 * sms + 128 + 37                                   # two chunks, the second one ragged
+    ids, _ = synth.make_sequences(cfg, num_users=512, seed=11)
+    ids = ids.repeat((B + 511) // 512, 1)[:B]
+    ids[512:, -1] = torch.randint(1, cfg.num_items, (B - 512,), generator=torch.Generator().manual_seed(3))
+    x = ids.cuda()
+    u, u16 = m.encode(x, want_bf16=True)
+    big = m.retrieve(x, k=20, precision="bf16", u=u, u_bf16=u16)
+    big_i, big_s = big["ids"].clone(), big["scores"].clone()
+    for lo in (0, 128 * sms - 64, B - 300):                   # first chunk, across the boundary, ragged tail
+        hi = min(lo + 300, B)
+        ref = m.retrieve(x[lo:hi], k=20, precision="bf16", u=u[lo:hi].contiguous(), u_bf16=u16[lo:hi].contiguous())
+        assert torch.equal(ref["ids"], big_i[lo:hi]) and torch.equal(ref["scores"], big_s[lo:hi])
+
+
+def test_data_parallel_exchange_records_on_one_device(games_model):
+    """The data-parallel path scores users it never saw the ids of: user state + sorted exclusion list + filter
+    (the all-gathered exchange record) must give the same lists as the ids themselves, and the [B, 2, k]
+    row payload + merge_rows must equal the plain result."""
+    from llamarec_b200.sharded import CudaBackend
+    m, sd, cfg = games_model
+    ids, labels = synth.make_sequences(cfg, num_users=640, seed=13)
+    x = ids.cuda()
+    ref = m.retrieve(x, k=20, precision="bf16", labels=labels.cuda(), ks=[1, 5, 10, 20])
+    ref_i, ref_s, ref_sums = ref["ids"].clone(), ref["scores"].clone(), ref["metric_sums"].clone()
+    R = 2
+    backs = []
+    for r in range(R):
+        mm = LRURec(_args(cfg.num_items)); mm.load_state_dict(sd); mm = mm.cuda().eval()
+        backs.append(CudaBackend(mm, r, R, precision="bf16"))
+    st = backs[0].encode_states(x, True)
+    rows = [b.local_topk_rows(st["state"], st["excl"], st["bloom"], st["excl_stride"], 20).clone() for b in backs]
+    out = backs[0].merge_rows(torch.stack(rows), 20, labels.cuda(), [1, 5, 10, 20])
+    assert torch.equal(out["ids"], ref_i) and torch.equal(out["scores"], ref_s)
+    assert torch.allclose(out["metric_sums"], ref_sums, rtol=1e-5)
+
+
 def test_full_size_10m_catalogue_properties():
     """BASELINE config 4 (10M items, batch 4096): properties that need no CPU pass over the table, plus an
     exact check of 4 users against a plain torch fp32 matmul over the same bf16 operands."""

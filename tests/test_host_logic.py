@@ -142,6 +142,20 @@ class OracleBackend:
         ts, ti = O.topk_sorted(s, k)
         return torch.stack((ts.contiguous().view(torch.int32), (ti + self.lo).to(torch.int32)))
 
+    # data-parallel users: opaque exchange records (the retriever only moves them)
+    def encode_states(self, x, exclude_history):
+        u = O.encode(x, self.sd)
+        return {"state": u, "excl": x.to(torch.int32) if exclude_history else None, "bloom": None,
+                "excl_stride": x.shape[1], "u": u}
+
+    def local_topk_rows(self, state, excl, bloom, excl_stride, k):
+        p = self.local_topk_packed(excl if excl is not None else torch.zeros(state.shape[0], 0, dtype=torch.int32),
+                                   state, k, excl is not None)
+        return p.permute(1, 0, 2).contiguous()                           # [B, 2, k]
+
+    def merge_rows(self, recv, k, labels, ks):
+        return self.merge_packed(recv.permute(0, 2, 1, 3), k, labels, ks)   # [R, 2, b, k]
+
     def merge_packed(self, gathered, k, labels, ks):
         s_all = gathered[:, 0].contiguous().view(torch.float32)
         i_all = gathered[:, 1].contiguous()
@@ -164,8 +178,12 @@ def _worker(rank, world, port, sd_np, ids_np, q):
     x = torch.from_numpy(ids_np)
     r = ShardedRetriever(OracleBackend(sd, rank, world))
     out = r.retrieve(x, k=20, exclude_history=True)
+    # data-parallel users: each rank brings its own slice of the batch
+    b = x.shape[0] // world
+    dp = r.retrieve_dp(x[rank * b:(rank + 1) * b], k=20, exclude_history=True)
+    q.put(("dp", rank, dp["scores"].numpy(), dp["ids"].numpy()))
     if rank == 0:
-        q.put((out["scores"].numpy(), out["ids"].numpy(), out["u"].numpy()))
+        q.put(("full", out["scores"].numpy(), out["ids"].numpy(), out["u"].numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -179,12 +197,17 @@ def test_sharded_retrieval_two_ranks_gloo(golden_sd):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, sd_np, ids, q)) for r in range(2)]
     for p in procs:
         p.start()
-    s, i, u = q.get(timeout=120)
+    msgs = [q.get(timeout=120) for _ in range(3)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     x = torch.from_numpy(ids)
     ref_s, ref_i = O.retrieve(x, golden_sd, 20)
+    (_, s, i, u), = [m for m in msgs if m[0] == "full"]
+    b = x.shape[0] // 2
+    for _, rank, ds, di in [m for m in msgs if m[0] == "dp"]:
+        assert np.array_equal(di, ref_i[rank * b:(rank + 1) * b].numpy().astype(np.int32))
+        np.testing.assert_allclose(ds, ref_s[rank * b:(rank + 1) * b].numpy(), atol=1e-6)
     np.testing.assert_allclose(u, O.encode(x, golden_sd).numpy(), atol=1e-6)
     assert np.array_equal(i, ref_i.numpy().astype(np.int32))
     np.testing.assert_allclose(s, ref_s.numpy(), atol=1e-6)

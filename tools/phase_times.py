@@ -53,3 +53,26 @@ print("final merge+metrics us:", round(timeit(fm)))
 t0 = time.perf_counter()
 for _ in range(50): m.retrieve(ids, k=K, u=u_full, precision="bf16", packed_out=payload)
 print("python launch cost of retrieve() us:", round((time.perf_counter() - t0) / 50 * 1e6)); torch.cuda.synchronize()
+
+# ---- weak scaling (data-parallel users): one rank scores R*B users against its 1/R of the rows ----
+from llamarec_b200.sharded import CudaBackend
+be = CudaBackend(m, 0, R, precision="bf16")
+sts = []
+for r in range(R):
+    xr, _ = synth.make_sequences_fast(B, N, L, seed=42 + r)
+    st = be.encode_states(xr.to(dev), True)
+    sts.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()})
+state = torch.cat([s["state"] for s in sts]); excl = torch.cat([s["excl"] for s in sts]); bloom = torch.cat([s["bloom"] for s in sts])
+stride = sts[0]["excl_stride"]
+print(f"weak R={R}: users scored per rank={state.shape[0]}")
+print("encode_states (own 4096) us:", round(timeit(lambda: be.encode_states(ids, True))))
+print("score R*B + local merge  us:", round(timeit(lambda: be.local_topk_rows(state, excl, bloom, stride, K), n=10)))
+m.profile_events = []
+for _ in range(5): be.local_topk_rows(state, excl, bloom, stride, K)
+torch.cuda.synchronize()
+print("  score call only        us:", round(sum(a.elapsed_time(b) for a, b in m.profile_events) / len(m.profile_events) * 1e3))
+m.profile_events = None
+recv = torch.empty(R, B, 2, K, dtype=torch.int32, device=dev)
+rows = be.local_topk_rows(state, excl, bloom, stride, K)
+for r in range(R): recv[r].copy_(rows[:B])
+print("final merge (own 4096, R lists) us:", round(timeit(lambda: be.merge_rows(recv, K, labels, [1, 5, 10, 20]))))

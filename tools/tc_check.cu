@@ -34,6 +34,7 @@
 extern "C" void lrb_debug_set_score_mode(int m);
 extern "C" void lrb_debug_set_stats(long long* p);
 extern "C" void lrb_debug_set_scout(int t);
+extern "C" void lrb_debug_set_pair_drain(int v);
 
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
@@ -355,7 +356,8 @@ int main(int argc, char** argv) {
     int rows = argc > 3 ? atoi(argv[3]) : 2500000;
     int K = argc > 4 ? atoi(argv[4]) : 20;
     int mode = argc > 5 ? atoi(argv[5]) : 0;
-    if (argc > 6) { lrb_debug_set_scout(atoi(argv[6])); printf("scout tiles %d\n", atoi(argv[6])); }
+    if (argc > 6 && atoi(argv[6]) >= 0) { lrb_debug_set_scout(atoi(argv[6])); printf("scout tiles %d\n", atoi(argv[6])); }
+    if (argc > 7) { lrb_debug_set_pair_drain(atoi(argv[7])); printf("pair drain %d\n", atoi(argv[7])); }
     lrb_debug_set_score_mode(mode);
     if (mode) printf("debug mode %d\n", mode);
     time_topk(B, rows, K, true, true);
