@@ -217,7 +217,7 @@ def run_product(args, rank, world, local_rank):
 
     # one sampler (rank 0's GPU) is enough and keeps driver polling away from the other ranks
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("LRB_BENCH_NO_SAMPLER"):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(ids_dev)
@@ -271,6 +271,20 @@ def run_product(args, rank, world, local_rank):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+
+    if os.environ.get("LRB_BENCH_PHASES") and weak:
+        # developer aid: per-phase GPU times of the data-parallel step (rank 0, stderr)
+        retr.phase_events = []
+        for _ in range(10):
+            step(ids_dev)
+        barrier()
+        evs, acc = retr.phase_events, {}
+        retr.phase_events = None
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            if n1 != "begin":
+                acc.setdefault(n1, []).append(e0.elapsed_time(e1))
+        if rank == 0:
+            print({k: round(1e3 * statistics.mean(v)) for k, v in acc.items()}, "us per phase", file=sys.stderr)
 
     t = torch.tensor([ms_total, e2e_s, statistics.mean(score_ms)], dtype=torch.float64, device=device)
     if world > 1:

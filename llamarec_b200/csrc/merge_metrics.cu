@@ -20,7 +20,8 @@ namespace lrb {
 namespace mm {
 
 constexpr int WARPS = 8;
-constexpr int PER_LANE = 16;   // register-resident entries per lane (512 per user)
+constexpr int MAX_PER_LANE = 16;   // register-resident entries per lane (up to 512 per user); the kernel is
+                                   // instantiated for 2/4/8/16 so that narrow fan-in does not pay for 16
 constexpr int MAX_KS = 8;
 
 struct Params {
@@ -60,6 +61,7 @@ LRB_DEVINL Best warp_best(float s, int id, int lane) {
   return b;
 }
 
+template <int PER_LANE>
 __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params p) {
   __shared__ float s_sums[WARPS][3 * MAX_KS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,7 +221,12 @@ extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_i
   p.out_stride = out_stride > 0 ? out_stride : K_out;
   p.metric_sums = (labels && n_ks > 0) ? metric_sums : nullptr;
   const int grid = (B + mm::WARPS - 1) / mm::WARPS;
-  mm::merge_metrics_kernel<<<grid, mm::WARPS * 32, 0, as_stream(stream)>>>(p);
+  const long long total = static_cast<long long>(n_lists) * K_in;
+  cudaStream_t st = as_stream(stream);
+  if (total <= 64) mm::merge_metrics_kernel<2><<<grid, mm::WARPS * 32, 0, st>>>(p);
+  else if (total <= 128) mm::merge_metrics_kernel<4><<<grid, mm::WARPS * 32, 0, st>>>(p);
+  else if (total <= 256) mm::merge_metrics_kernel<8><<<grid, mm::WARPS * 32, 0, st>>>(p);
+  else mm::merge_metrics_kernel<mm::MAX_PER_LANE><<<grid, mm::WARPS * 32, 0, st>>>(p);
   LRB_CUDA_TRY(cudaGetLastError());
   return LRB_OK;
 }

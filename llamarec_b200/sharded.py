@@ -125,6 +125,7 @@ class ShardedRetriever:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._bufs = {}
+        self.phase_events = None     # optional list: retrieve_dp appends (phase name, CUDA event) pairs
         self._coalesce = dist.is_initialized() and dist.get_backend(group) == "nccl"
 
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
@@ -134,6 +135,12 @@ class ShardedRetriever:
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t, group=self.group)   # concatenated along dim 0 (gloo and nccl)
         return out.reshape((self.world,) + tuple(t.shape))
+
+    def _mark(self, name: str) -> None:
+        if self.phase_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_events.append((name, ev))
 
     def _all_gather_many(self, tensors):
         """All-gathers several per-rank tensors (None entries pass through) as ONE collective launch where the
@@ -170,9 +177,14 @@ class ShardedRetriever:
         """x: THIS rank's users [b, L] (every rank passes the same b; labels likewise [b]).  Returns the final
         top-k of the local users against the WHOLE catalogue (+ metric sums over the local users)."""
         b = x.shape[0]
+        mark = self._mark
+        mark("begin")
         st = self.backend.encode_states(x, exclude_history)
+        mark("encode")
         state, excl, bloom = self._all_gather_many([st["state"], st["excl"], st["bloom"]])
+        mark("all_gather")
         payload = self.backend.local_topk_rows(state, excl, bloom, st["excl_stride"], k)      # [R*b, 2, k]
+        mark("score+local_merge")
         if self.world > 1:
             key = ("a2a", tuple(payload.shape), str(payload.device))
             recv = self._bufs.get(key)
@@ -182,7 +194,9 @@ class ShardedRetriever:
             dist.all_to_all_single(recv, payload, group=self.group)
         else:
             recv = payload
+        mark("all_to_all")
         out = self.backend.merge_rows(recv.view(self.world, b, 2, k), k, labels, ks)
+        mark("merge")
         out["u"] = st["u"]
         return out
 
