@@ -200,7 +200,7 @@ def run_product(args, rank, world, local_rank):
     ks = [1, 5, 10, 20]
 
     if world > 1:
-        retr = ShardedRetriever(CudaBackend(model, rank, world, precision="bf16"))
+        retr = ShardedRetriever(CudaBackend(model, rank, world, precision="bf16"), exchange=args.exchange)
         fn = retr.retrieve_dp if weak else retr.retrieve
         step = lambda x: fn(x, k=TOPK, exclude_history=True, labels=labels_dev, ks=ks)
         rows = shard_range(N_ITEMS + 1, rank, world)
@@ -316,8 +316,11 @@ def run_product(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "batch_per_gpu": BATCH if (weak or world == 1) else BATCH // world,
                    "global_batch": global_batch, "max_len": MAX_LEN, "k": TOPK,
-                   "parallelism": (f"item table row-sharded x{world}; users data-parallel ({BATCH} per GPU); all-gather of "
-                                   f"user states, all-to-all of local top-{TOPK} lists" if weak else
+                   "parallelism": (f"item table row-sharded x{world}; users data-parallel ({BATCH} per GPU); user states "
+                                   f"gathered and local top-{TOPK} lists scattered to their owners by "
+                                   + ("the kernels' own stores into peer memory over NVLink" if retr._peer and all(
+                                       v is not None for v in retr._peer.values()) else "NCCL all-gather / all-to-all")
+                                   if weak else
                                    f"item table row-sharded x{world}, same {BATCH} users on every rank, batch-sharded encoder"
                                    if world > 1 else "single GPU"),
                    "l2": "item table (1.28 GB bf16) is 10x larger than L2; no flush needed",
@@ -352,6 +355,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
+                    help="N > 1, weak scaling: stores into peer memory (default when available) or NCCL collectives")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 4096 users per GPU (default), strong = 4096 users in total")
     ap.add_argument("--skip-cpu-baseline", action="store_true",

@@ -155,6 +155,29 @@ int lrb_merge_metrics(const float* list_scores, const int32_t* list_ids, const i
                       int64_t out_stride, int32_t* label_rank, float* metric_sums, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Peer-memory exchange of the row-sharded, data-parallel retrieval step (one process per GPU; the
+ * buffers are mapped into every process of the node over NVLink/NVSwitch).  The reference has no
+ * multi-device retrieval path; these replace the all-gather of user states
+ * and the all-to-all of local top-K lists a collective library would run around lrb_score_topk.
+ *
+ * lrb_peer_push: "all-gather by stores".  Copies n_arrays local arrays (bytes_host[a] bytes each, a
+ *   multiple of 16) to n_dst destinations each: dst_host[a*n_dst + d] is where array a lands on
+ *   destination d (this rank's slot of peer d's gather buffer; may be local or peer-mapped memory).
+ * lrb_merge_metrics_scatter: lrb_merge_metrics whose output rows are scattered by owner: user b's
+ *   merged list goes to row (b % users_per_dst) of destination b / users_per_dst
+ *   (dst_scores_host[d] / dst_ids_host[d], rows out_stride elements apart) -- the all-to-all fused
+ *   into the merge that produces its payload.  No labels / metrics in this variant.
+ * Ordering between ranks (a barrier after the stores, double-buffered destinations) is the caller's.
+ * ------------------------------------------------------------------------------------------ */
+int lrb_peer_push(const void* const* src_host, const size_t* bytes_host, int n_arrays,
+                  void* const* dst_host, int n_dst, void* stream);
+int lrb_merge_metrics_scatter(const float* list_scores, const int32_t* list_ids, const int32_t* list_cnt,
+                              int n_lists, int64_t stride_list, int64_t stride_user, int64_t cnt_stride_list,
+                              int64_t cnt_stride_user, int K_in, int B, int K_out,
+                              float* const* dst_scores_host, int32_t* const* dst_ids_host, int n_dst,
+                              int users_per_dst, int64_t out_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage-2 verbalizer tail.  Replaces lm_head on the last position (model/llm.py:113-114,131) and
  * ManualVerbalizer.process_logits (trainer/verb.py:546-586: project -> [normalize -> log] ->
  * aggregate) by computing only the label-word rows of the lm_head.

@@ -23,6 +23,7 @@ constexpr int WARPS = 8;
 constexpr int MAX_PER_LANE = 16;   // register-resident entries per lane (up to 512 per user); the kernel is
                                    // instantiated for 2/4/8/16 so that narrow fan-in does not pay for 16
 constexpr int MAX_KS = 8;
+constexpr int MAX_DST = 16;    // scatter mode: destination buffers (ranks of one node)
 
 struct Params {
   const float* list_scores;
@@ -37,6 +38,12 @@ struct Params {
   float* top_scores;           // [B][K_out], rows out_stride elements apart
   int* top_ids;                // [B][K_out], rows out_stride elements apart
   long long out_stride;
+  // scatter mode (users_per_dst > 0): user b's list goes to row (b % users_per_dst) of destination
+  // b / users_per_dst -- the recv buffer of the rank that owns the user, written over NVLink; this is the
+  // all-to-all of the row-sharded retrieval step fused into the merge that produces its payload.
+  float* dst_scores[MAX_DST];
+  int* dst_ids[MAX_DST];
+  int users_per_dst;
   int* label_rank;             // [B] (may be null)
   float* metric_sums;          // [3*n_ks] (may be null)
 };
@@ -96,6 +103,14 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
       }
     }
 
+    float* out_s = p.top_scores + static_cast<size_t>(b) * p.out_stride;
+    int* out_i = p.top_ids + static_cast<size_t>(b) * p.out_stride;
+    if (p.users_per_dst > 0) {
+      const int d = b / p.users_per_dst;
+      const size_t row = static_cast<size_t>(b - d * p.users_per_dst);
+      out_s = p.dst_scores[d] + row * p.out_stride;
+      out_i = p.dst_ids[d] + row * p.out_stride;
+    }
     int my_rank = -1;
     const long long label = p.labels ? p.labels[b] : -1;
     // floor for the global-memory path: entries must be strictly "after" the previous winner
@@ -157,8 +172,8 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
       prev_id = w_id;
       const bool valid = w_id != INT_MAX;
       if (lane == 0) {
-        p.top_scores[static_cast<size_t>(b) * p.out_stride + k] = valid ? w_s : -INFINITY;
-        p.top_ids[static_cast<size_t>(b) * p.out_stride + k] = valid ? w_id : -1;
+        out_s[k] = valid ? w_s : -INFINITY;
+        out_i[k] = valid ? w_id : -1;
       }
       if (valid && my_rank < 0 && static_cast<long long>(w_id) == label) my_rank = k;
     }
@@ -195,21 +210,22 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
 }  // namespace mm
 }  // namespace lrb
 
-extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_ids, const int32_t* list_cnt,
-                                 int n_lists, int64_t stride_list, int64_t stride_user,
-                                 int64_t cnt_stride_list, int64_t cnt_stride_user, int K_in, int B, int K_out,
-                                 const int64_t* labels, const int32_t* ks_host, int n_ks, float* top_scores,
-                                 int32_t* top_ids, int64_t out_stride, int32_t* label_rank, float* metric_sums,
-                                 void* stream) {
+namespace {
+int merge_launch(const float* list_scores, const int32_t* list_ids, const int32_t* list_cnt, int n_lists,
+                 int64_t stride_list, int64_t stride_user, int64_t cnt_stride_list, int64_t cnt_stride_user,
+                 int K_in, int B, int K_out, const int64_t* labels, const int32_t* ks_host, int n_ks,
+                 float* top_scores, int32_t* top_ids, float* const* dst_scores_host,
+                 int32_t* const* dst_ids_host, int n_dst, int users_per_dst, int64_t out_stride,
+                 int32_t* label_rank, float* metric_sums, void* stream) {
   using namespace lrb;
   int rc = check_arch();
   if (rc != LRB_OK) return rc;
-  LRB_REQUIRE(list_scores && list_ids && top_scores && top_ids, "lrb_merge_metrics: null pointer");
+  LRB_REQUIRE(list_scores && list_ids, "lrb_merge_metrics: null pointer");
   LRB_REQUIRE(n_lists >= 1 && K_in >= 1 && B >= 1 && K_out >= 1, "lrb_merge_metrics: bad shape");
   LRB_REQUIRE(n_ks >= 0 && n_ks <= mm::MAX_KS, "lrb_merge_metrics: at most %d cut-offs", mm::MAX_KS);
   LRB_REQUIRE(n_ks == 0 || ks_host != nullptr, "lrb_merge_metrics: ks missing");
   LRB_REQUIRE(out_stride == 0 || out_stride >= K_out, "lrb_merge_metrics: out_stride must be 0 or >= K_out");
-  mm::Params p;
+  mm::Params p = {};
   p.list_scores = list_scores; p.list_ids = list_ids; p.list_cnt = list_cnt; p.n_lists = n_lists;
   p.stride_list = stride_list; p.stride_user = stride_user;
   p.cnt_stride_list = cnt_stride_list; p.cnt_stride_user = cnt_stride_user;
@@ -219,6 +235,21 @@ extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_i
   p.n_ks = labels ? n_ks : 0;
   p.top_scores = top_scores; p.top_ids = top_ids; p.label_rank = label_rank;
   p.out_stride = out_stride > 0 ? out_stride : K_out;
+  p.users_per_dst = 0;
+  if (n_dst > 0) {
+    LRB_REQUIRE(n_dst <= mm::MAX_DST && users_per_dst >= 1 && dst_scores_host && dst_ids_host,
+                "lrb_merge_metrics_scatter: 1..%d destinations with users_per_dst >= 1", mm::MAX_DST);
+    LRB_REQUIRE(static_cast<long long>(n_dst) * users_per_dst >= B,
+                "lrb_merge_metrics_scatter: %d destinations x %d users do not cover B=%d", n_dst, users_per_dst, B);
+    for (int d = 0; d < n_dst; ++d) {
+      LRB_REQUIRE(dst_scores_host[d] && dst_ids_host[d], "lrb_merge_metrics_scatter: null destination %d", d);
+      p.dst_scores[d] = dst_scores_host[d];
+      p.dst_ids[d] = dst_ids_host[d];
+    }
+    p.users_per_dst = users_per_dst;
+  } else {
+    LRB_REQUIRE(top_scores && top_ids, "lrb_merge_metrics: null output pointer");
+  }
   p.metric_sums = (labels && n_ks > 0) ? metric_sums : nullptr;
   const int grid = (B + mm::WARPS - 1) / mm::WARPS;
   const long long total = static_cast<long long>(n_lists) * K_in;
@@ -229,4 +260,27 @@ extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_i
   else mm::merge_metrics_kernel<mm::MAX_PER_LANE><<<grid, mm::WARPS * 32, 0, st>>>(p);
   LRB_CUDA_TRY(cudaGetLastError());
   return LRB_OK;
+}
+}  // namespace
+
+extern "C" int lrb_merge_metrics(const float* list_scores, const int32_t* list_ids, const int32_t* list_cnt,
+                                 int n_lists, int64_t stride_list, int64_t stride_user,
+                                 int64_t cnt_stride_list, int64_t cnt_stride_user, int K_in, int B, int K_out,
+                                 const int64_t* labels, const int32_t* ks_host, int n_ks, float* top_scores,
+                                 int32_t* top_ids, int64_t out_stride, int32_t* label_rank, float* metric_sums,
+                                 void* stream) {
+  return merge_launch(list_scores, list_ids, list_cnt, n_lists, stride_list, stride_user, cnt_stride_list,
+                      cnt_stride_user, K_in, B, K_out, labels, ks_host, n_ks, top_scores, top_ids, nullptr, nullptr,
+                      0, 0, out_stride, label_rank, metric_sums, stream);
+}
+
+extern "C" int lrb_merge_metrics_scatter(const float* list_scores, const int32_t* list_ids,
+                                         const int32_t* list_cnt, int n_lists, int64_t stride_list,
+                                         int64_t stride_user, int64_t cnt_stride_list, int64_t cnt_stride_user,
+                                         int K_in, int B, int K_out, float* const* dst_scores_host,
+                                         int32_t* const* dst_ids_host, int n_dst, int users_per_dst,
+                                         int64_t out_stride, void* stream) {
+  return merge_launch(list_scores, list_ids, list_cnt, n_lists, stride_list, stride_user, cnt_stride_list,
+                      cnt_stride_user, K_in, B, K_out, nullptr, nullptr, 0, nullptr, nullptr, dst_scores_host,
+                      dst_ids_host, n_dst, users_per_dst, out_stride, nullptr, nullptr, stream);
 }

@@ -135,7 +135,8 @@ class LRURec(nn.Module):
                  labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
                  precision: str = "auto", u: Optional[torch.Tensor] = None,
                  u_bf16: Optional[torch.Tensor] = None, merge: bool = True,
-                 packed_out: Optional[torch.Tensor] = None, seq: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                 packed_out: Optional[torch.Tensor] = None, seq: Optional[dict] = None,
+                 scatter: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """encode -> catalogue score -> (history mask) -> top-k -> (metrics), all on device.
 
         Replaces calculate_metrics / the per-user loop of generate_candidates (trainer/lru.py:30-42,
@@ -146,7 +147,9 @@ class LRURec(nn.Module):
         With merge=False the per-split partial lists are returned instead (used by the sharded path).
         `seq` (optional) is a prepared descriptor holding `excl_sorted`/`excl_bloom`/`excl_stride` for the
         rows of `u`; with it `x` may be None -- the sharded path scores user states and exclusion lists
-        that were encoded on other ranks.
+        that were encoded on other ranks.  `scatter` ({"dst_scores": [...], "dst_ids": [...], "users_per_dst": n,
+        "out_stride": s} of raw device/peer addresses) makes the merge write every user's list straight into
+        the buffer of the rank that owns the user (lrb_merge_metrics_scatter).
         """
         lib = _lib.load()
         c = self._prepare()
@@ -193,7 +196,8 @@ class LRURec(nn.Module):
             self.profile_events.append((ev0, ev1))
         if not merge:
             return {"part_scores": part_s, "part_ids": part_i, "part_cnt": part_c, "u": u}
-        out = merge_lists(part_s, part_i, part_c, k_out=k, labels=labels, ks=ks, packed_out=packed_out)
+        out = merge_lists(part_s, part_i, part_c, k_out=k, labels=labels, ks=ks, packed_out=packed_out,
+                          scatter=scatter)
         out["u"] = u
         return out
 
@@ -297,7 +301,7 @@ class LRURec(nn.Module):
 def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Optional[torch.Tensor], k_out: int,
                 labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
                 layout: str = "user_major", packed_out: Optional[torch.Tensor] = None,
-                strides: Optional[tuple] = None) -> Dict[str, torch.Tensor]:
+                strides: Optional[tuple] = None, scatter: Optional[dict] = None) -> Dict[str, torch.Tensor]:
     """Fused k-way merge + metrics (lrb_merge_metrics).
 
     layout 'user_major': lists are [B, S, K] (output of lrb_score_topk);
@@ -317,6 +321,17 @@ def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Opt
         stride_list, stride_user = strides
     else:
         list_scores, list_ids = list_scores.contiguous(), list_ids.contiguous()
+    if scatter is not None:
+        # all-to-all fused into the merge: rows go to the owner rank's recv buffer (peer-mapped addresses)
+        n_dst = len(scatter["dst_scores"])
+        arr_s = (_lib.ctypes.c_void_p * n_dst)(*scatter["dst_scores"])
+        arr_i = (_lib.ctypes.c_void_p * n_dst)(*scatter["dst_ids"])
+        _lib.check(lib.lrb_merge_metrics_scatter(
+            list_scores.data_ptr(), list_ids.data_ptr(),
+            _lib.ptr(list_cnt.contiguous()) if list_cnt is not None else None, S, stride_list, stride_user, cnt_sl,
+            cnt_su, K, B, k_out, arr_s, arr_i, n_dst, int(scatter["users_per_dst"]), int(scatter["out_stride"]),
+            _lib.stream_handle()))
+        return {}
     ks = list(ks) if ks is not None else []
     out_stride = 0
     if packed_out is not None and packed_out.shape[0] == 2 and packed_out.dim() == 3 and packed_out.shape[1] == B:

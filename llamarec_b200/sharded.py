@@ -20,6 +20,14 @@ Two batch layouts are supported:
       3. ONE all-to-all: the lists of rank j's users go to rank j                   [R x b x 2 x k x 4 bytes]
       4. merge the R lists of the local users (fused with the metrics)             (no communication)
 
+On NVLink (NCCL process group + CUDA backend) steps 1 and 3 of `retrieve_dp` do not go through a collective
+library at all: every rank STORES its exchange records into its slot of every peer's gather buffer
+(`lrb_peer_push`), and the local merge kernel scatters each user's list straight into the recv buffer of
+the rank that owns the user (`lrb_merge_metrics_scatter`) -- the transfer is the kernel's own epilogue.
+The buffers live in symmetric memory (peer-mapped over NVLink/NVSwitch), are double buffered, and one
+signal-pad barrier per exchange orders the ranks.  Without symmetric memory (gloo on CPU in the tests) the
+same step runs on `all_gather_into_tensor` / `all_to_all_single`.
+
 The numerical work is delegated to a backend object so that the plumbing (ranges, padding, gather
 layout) can be exercised on CPU with gloo in tests; the product backend drives the CUDA kernels.
 """
@@ -80,9 +88,19 @@ class CudaBackend:
         return {"state": u16 if prec == 0 else u, "excl": seq["excl_sorted"], "bloom": seq["excl_bloom"],
                 "excl_stride": seq["excl_stride"], "u": u}
 
-    def local_topk_rows(self, state: torch.Tensor, excl, bloom, excl_stride: int, k: int) -> torch.Tensor:
-        """All R*b users against this rank's rows -> int32 [R*b, 2, k]: per user scores (bit pattern), ids."""
+    supports_peer_exchange = True
+
+    def local_topk_rows(self, state: torch.Tensor, excl, bloom, excl_stride: int, k: int,
+                        scatter: Optional[dict] = None) -> Optional[torch.Tensor]:
+        """All R*b users against this rank's rows -> int32 [R*b, 2, k]: per user scores (bit pattern), ids.
+        With `scatter` the rows are written into the owners' recv buffers instead (nothing is returned)."""
         B = state.shape[0]
+        if scatter is not None and self.rows[1] > self.rows[0]:
+            seq = {"excl_sorted": excl, "excl_bloom": bloom, "excl_stride": excl_stride}
+            kw = {"u_bf16": state} if state.dtype == torch.bfloat16 else {"u": state}
+            self.model.retrieve(None, k=k, exclude_history=excl is not None, precision=self.precision, seq=seq,
+                                scatter=scatter, **kw)
+            return None
         key = ("rows", B, k, str(state.device))
         buf = self._packed.get(key)
         if buf is None:
@@ -118,10 +136,57 @@ class CudaBackend:
                            strides=(2 * B * K, K))
 
 
+class PeerExchange:
+    """Symmetric-memory buffers of one (b, k, record layout) configuration: per parity a gather region
+    (state | exclusion list | filter, R*b rows each) and a recv region [R][b][2][k] int32."""
+
+    def __init__(self, group, rank: int, world: int, device, b: int, k: int, rec_bytes: Sequence[int]):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.b, self.k = rank, world, b, k
+        self.rec_bytes = list(rec_bytes)
+        al = lambda n: (n + 255) // 256 * 256
+        off = 0
+        self.gather_off, self.recv_off = [], []
+        for _ in range(2):
+            offs = []
+            for rb in self.rec_bytes:
+                offs.append(off)
+                off += al(world * b * rb)
+            self.gather_off.append(offs)
+        for _ in range(2):
+            self.recv_off.append(off)
+            off += al(world * b * 2 * k * 4)
+        self.total = off
+        self.buf = symm.empty(self.total, dtype=torch.uint8, device=device)
+        name = (group if group is not None else dist.group.WORLD).group_name
+        self.hdl = symm.rendezvous(self.buf, name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def barrier(self, channel: int) -> None:
+        self.hdl.barrier(channel=channel)
+
+    def gather_view(self, parity: int, a: int, dtype, row_shape) -> torch.Tensor:
+        n = self.world * self.b * self.rec_bytes[a]
+        o = self.gather_off[parity][a]
+        return self.buf[o:o + n].view(dtype).view((self.world * self.b,) + tuple(row_shape))
+
+    def recv_view(self, parity: int) -> torch.Tensor:
+        n = self.world * self.b * 2 * self.k * 4
+        o = self.recv_off[parity]
+        return self.buf[o:o + n].view(torch.int32).view(self.world, self.b, 2, self.k)
+
+
 class ShardedRetriever:
-    def __init__(self, backend, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, backend, group: Optional[dist.ProcessGroup] = None, exchange: str = "auto"):
+        """exchange: 'peer' (stores into symmetric memory, needs NCCL + CUDA), 'collective'
+        (torch.distributed all-gather / all-to-all), or 'auto' (peer when available)."""
         self.backend = backend
         self.group = group
+        if exchange not in ("auto", "peer", "collective"):
+            raise ValueError(f"unknown exchange {exchange!r}")
+        self.exchange = exchange
+        self._peer = {}
+        self._parity = 0
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._bufs = {}
@@ -141,6 +206,64 @@ class ShardedRetriever:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self.phase_events.append((name, ev))
+
+    def _peer_exchange(self, b: int, k: int, st: dict) -> Optional[PeerExchange]:
+        if self.exchange == "collective" or not getattr(self.backend, "supports_peer_exchange", False):
+            return None
+        if self.exchange == "auto" and not (dist.is_initialized() and dist.get_backend(self.group) == "nccl"):
+            return None
+        arrays = [t for t in (st["state"], st["excl"], st["bloom"]) if t is not None]
+        rec = tuple(t[0].numel() * t.element_size() for t in arrays)
+        key = (b, k, rec, str(arrays[0].dtype))
+        if key not in self._peer:
+            try:
+                self._peer[key] = PeerExchange(self.group, self.rank, self.world, arrays[0].device, b, k, rec)
+            except Exception as e:                      # symmetric memory not available on this system
+                if self.exchange == "peer":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e!r}); using torch.distributed collectives")
+                self._peer[key] = None
+        return self._peer[key]
+
+    def _retrieve_dp_peer(self, px: PeerExchange, st: dict, b: int, k: int, labels, ks):
+        from . import _lib
+        lib = _lib.load()
+        mark = self._mark
+        par = self._parity
+        self._parity ^= 1
+        arrays = [t for t in (st["state"], st["excl"], st["bloom"]) if t is not None]
+        n_arr, R = len(arrays), self.world
+        # 1. all-gather by stores: my b records go to slot `rank` of every rank's gather region
+        src = (_lib.ctypes.c_void_p * n_arr)(*[t.data_ptr() for t in arrays])
+        nbytes = (_lib.ctypes.c_size_t * n_arr)(*[b * rb for rb in px.rec_bytes])
+        dst = (_lib.ctypes.c_void_p * (n_arr * R))(*[
+            px.ptrs[d] + px.gather_off[par][a] + self.rank * b * px.rec_bytes[a]
+            for a in range(n_arr) for d in range(R)])
+        _lib.check(lib.lrb_peer_push(src, nbytes, n_arr, dst, R, _lib.stream_handle()))
+        px.barrier(0)
+        mark("all_gather")
+        # 2. score all R*b users against the local rows; the local merge scatters each user's list to its owner
+        views = [px.gather_view(par, a, t.dtype, t.shape[1:]) for a, t in enumerate(arrays)]
+        state = views[0]
+        excl, bloom = (views[1], views[2]) if st["excl"] is not None else (None, None)
+        base = [px.ptrs[d] + px.recv_off[par] + self.rank * b * 2 * k * 4 for d in range(R)]
+        scatter = {"dst_scores": base, "dst_ids": [p + k * 4 for p in base], "users_per_dst": b,
+                   "out_stride": 2 * k}
+        rows = self.backend.local_topk_rows(state, excl, bloom, st["excl_stride"], k, scatter=scatter)
+        if rows is not None:                                # empty shard: nothing was scattered, hand out the fill
+            for d in range(R):
+                px.hdl.get_buffer(d, (px.total,), torch.uint8)[
+                    px.recv_off[par] + self.rank * b * 2 * k * 4:][:b * 2 * k * 4].view(torch.int32).copy_(
+                    rows[d * b:(d + 1) * b].reshape(-1))
+        mark("score+local_merge")
+        px.barrier(1)
+        mark("all_to_all")
+        # 3. merge the R lists of the local users
+        out = self.backend.merge_rows(px.recv_view(par), k, labels, ks)
+        mark("merge")
+        out["u"] = st["u"]
+        return out
 
     def _all_gather_many(self, tensors):
         """All-gathers several per-rank tensors (None entries pass through) as ONE collective launch where the
@@ -181,6 +304,9 @@ class ShardedRetriever:
         mark("begin")
         st = self.backend.encode_states(x, exclude_history)
         mark("encode")
+        px = self._peer_exchange(b, k, st) if self.world > 1 else None
+        if px is not None:
+            return self._retrieve_dp_peer(px, st, b, k, labels, ks)
         state, excl, bloom = self._all_gather_many([st["state"], st["excl"], st["bloom"]])
         mark("all_gather")
         payload = self.backend.local_topk_rows(state, excl, bloom, st["excl_stride"], k)      # [R*b, 2, k]

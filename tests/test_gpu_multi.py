@@ -40,6 +40,16 @@ dp = sh.retrieve_dp(ids[lo:lo + b].cuda(), k=20, labels=labels[lo:lo + b].cuda()
 assert torch.equal(dp["ids"], ref["ids"][lo:lo + b]), "dp ids differ"
 assert torch.equal(dp["scores"], ref["scores"][lo:lo + b]), "dp scores differ"
 assert torch.equal(dp["label_rank"], ref["label_rank"][lo:lo + b])
+assert sh._peer and all(v is not None for v in sh._peer.values()), "peer-memory exchange was not used"
+# same step on torch.distributed collectives, and the peer path again (double-buffer parity, 3 more steps)
+shc = ShardedRetriever(CudaBackend(m, rank, world, precision="bf16"), exchange="collective")
+dc = shc.retrieve_dp(ids[lo:lo + b].cuda(), k=20, labels=labels[lo:lo + b].cuda(), ks=[1, 5, 10, 20])
+assert torch.equal(dc["ids"], dp["ids"]) and torch.equal(dc["scores"], dp["scores"])
+for it in range(3):
+    sl = slice((lo + 7 * it) % 300, (lo + 7 * it) % 300 + b)
+    d2 = sh.retrieve_dp(ids[sl].cuda(), k=20, labels=labels[sl].cuda(), ks=[1, 5, 10, 20])
+    ref2 = ref_model.retrieve(ids[sl].cuda(), k=20, precision="bf16")
+    assert torch.equal(d2["ids"], ref2["ids"]) and torch.equal(d2["scores"], ref2["scores"]), f"peer step {it}"
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
