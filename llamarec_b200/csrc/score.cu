@@ -299,7 +299,7 @@ int make_tmap_bias_blocks(CUtensorMap* out, const void* ptr, unsigned long long 
 // `grid` counts MMA engines: CTAs for CG == 1, CTA pairs (clusters of 2) for CG == 2.
 template <int KMAX, int NS, bool kDense, int CG>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbias, const tc::ScoreParams& p,
-              int grid, cudaStream_t st) {
+              int grid, cudaStream_t st, bool overlap_prev = false) {
   using L = tc::SmemLayout<KMAX, NS, CG>;
   auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG>;
   LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
@@ -308,13 +308,22 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   cfg.blockDim = dim3(tc::THREADS);
   cfg.dynamicSmemBytes = L::kAlloc;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (overlap_prev) {   // may start while the previous chunk launch is still draining (see the kernel prologue)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CG > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   LRB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbias, p));
   LRB_CUDA_TRY(cudaGetLastError());
   return LRB_OK;
@@ -327,6 +336,8 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
 static int g_debug_mode = 0;
 static int g_debug_scout = -1;
 static int g_debug_pair_drain = 1;
+static int g_debug_overlap = 1;
+extern "C" void lrb_debug_set_overlap(int v) { g_debug_overlap = v; }
 static long long* g_debug_stats = nullptr;
 extern "C" void lrb_debug_set_pair_drain(int v) { g_debug_pair_drain = v; }
 extern "C" void lrb_debug_set_scout(int t) { g_debug_scout = t; }
@@ -336,6 +347,7 @@ extern "C" void lrb_debug_set_stats(long long* p) { g_debug_stats = p; }
 static const int g_debug_mode = 0;
 static const int g_debug_scout = -1;
 static const int g_debug_pair_drain = 1;
+static const int g_debug_overlap = 1;
 static long long* const g_debug_stats = nullptr;
 #endif
 
@@ -366,12 +378,31 @@ static size_t gslots_bytes(int B) {
   return ((m_tiles + 1) * lrb::tc::BM * max_slots * sizeof(int) + 255) & ~static_cast<size_t>(255);
 }
 
+// union-bound slots of one chunk launch of at most `cap` users (the worst case over smaller chunks: few user
+// tiles mean many streams, i.e. many slots per user)
+static size_t gslots_chunk_bytes(int cap) {
+  size_t mx = 0;
+  for (int b = lrb::tc::BM; b < cap + lrb::tc::BM; b += lrb::tc::BM) {
+    const size_t v = gslots_bytes(b < cap ? b : cap);
+    mx = v > mx ? v : mx;
+  }
+  return mx;
+}
+
+static size_t ring_bytes() {
+  int sms = lrb::device_sm_count();
+  if (sms <= 0) sms = 148;
+  return static_cast<size_t>(sms) * lrb::tc::EPI_THREADS * lrb::tc::RING_GROUPS * lrb::tc::RING_REC_BYTES;
+}
+
+// layout: [n_chunks x union-bound slots of one chunk][2 x candidate rings (consecutive chunk launches overlap)]
 size_t lrb_score_scratch_bytes(int B) {
   int sms = lrb::device_sm_count();
   if (sms <= 0) sms = 148;
-  const size_t ring = static_cast<size_t>(sms) * lrb::tc::EPI_THREADS * lrb::tc::RING_GROUPS *
-                      lrb::tc::RING_REC_BYTES;
-  return gslots_bytes(B) + ring;
+  if (B < 1) B = 1;
+  const int cap = lrb::users_per_launch(B, sms);
+  const size_t n_chunks = (static_cast<size_t>(B) + cap - 1) / cap;
+  return n_chunks * gslots_chunk_bytes(cap) + 2 * ring_bytes();
 }
 
 int lrb_score_topk(const void* u, const void* table, const float* bias_pad, const void* bias_blk,
@@ -424,7 +455,12 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
   }
   LRB_CUDA_TRY(cudaMemsetAsync(part_cnt, 0, static_cast<size_t>(B) * slots * sizeof(int), st));
   const int cap = users_per_launch(B, sms);
-  for (int c0 = 0; c0 < B; c0 += cap) {
+  const size_t n_chunks = (static_cast<size_t>(B) + cap - 1) / cap;
+  const size_t gs_chunk = gslots_chunk_bytes(cap);
+  // every chunk's union-bound slots are reset up front: nothing but kernels between the chunk launches
+  LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, n_chunks * gs_chunk, st));
+  int chunk_idx = 0;
+  for (int c0 = 0; c0 < B; c0 += cap, ++chunk_idx) {
     // one launch per user chunk (see users_per_launch); chunk-relative pointers
     const int Bc = B - c0 < cap ? B - c0 : cap;
     const int cg = cta_group_for(Bc, sms);
@@ -440,10 +476,10 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     p.excl_sorted = excl_sorted ? excl_sorted + static_cast<size_t>(c0) * excl_stride : nullptr;
     p.excl_bloom = excl_bloom ? excl_bloom + static_cast<size_t>(c0) * 4 : nullptr;
     p.excl_stride = excl_stride;
-    p.gslots = static_cast<int*>(scratch);
+    p.gslots = reinterpret_cast<int*>(static_cast<uint8_t*>(scratch) + chunk_idx * gs_chunk);
     p.gstride = d.slots;
     p.pair_drain = g_debug_pair_drain;
-    p.ring = static_cast<uint8_t*>(scratch) + gslots_bytes(B);
+    p.ring = static_cast<uint8_t*>(scratch) + n_chunks * gs_chunk + (chunk_idx & 1) * ring_bytes();
     {
       // entries each of the 2*s_full full-stream threads of a user must hold for the union bound
       const int c = d.s_full > 0 ? (K + 2 * d.s_full - 1) / (2 * d.s_full) : 99;
@@ -459,15 +495,15 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     p.slots = slots;
     p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
     p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
-    LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, static_cast<size_t>(d.m_tiles) * tc::BM * cg * d.slots * sizeof(int), st));
+    const bool ov = chunk_idx > 0 && g_debug_overlap;
     if (cg == 2) {
-      if (K <= 20) rc = launch_tc<20, 4, false, 2>(ta, tb2, tbias, p, d.grid, st);
-      else if (K <= 32) rc = launch_tc<32, 4, false, 2>(ta, tb2, tbias, p, d.grid, st);
-      else rc = launch_tc<50, 3, false, 2>(ta, tb2, tbias, p, d.grid, st);
+      if (K <= 20) rc = launch_tc<20, 4, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
+      else if (K <= 32) rc = launch_tc<32, 4, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
+      else rc = launch_tc<50, 3, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
     } else {
-      if (K <= 20) rc = launch_tc<20, 3, false, 1>(ta, tb1, tbias, p, d.grid, st);
-      else if (K <= 32) rc = launch_tc<32, 3, false, 1>(ta, tb1, tbias, p, d.grid, st);
-      else rc = launch_tc<50, 2, false, 1>(ta, tb1, tbias, p, d.grid, st);
+      if (K <= 20) rc = launch_tc<20, 3, false, 1>(ta, tb1, tbias, p, d.grid, st, ov);
+      else if (K <= 32) rc = launch_tc<32, 3, false, 1>(ta, tb1, tbias, p, d.grid, st, ov);
+      else rc = launch_tc<50, 2, false, 1>(ta, tb1, tbias, p, d.grid, st, ov);
     }
     if (rc != LRB_OK) return rc;
   }

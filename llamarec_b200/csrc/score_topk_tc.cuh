@@ -224,7 +224,10 @@ __device__ __noinline__ float topk_consider(float s, int gid, int row_limit_gid,
 // lane repeatedly picks the best remaining score of its current record with a branch-free argmax
 // and all lanes insert at the same time, so the insert cost is paid once per warp, not per lane.
 // -------------------------------------------------------------------------------------------
-constexpr int RING_GROUPS = 16;
+#ifndef LRB_RING_GROUPS
+#define LRB_RING_GROUPS 16
+#endif
+constexpr int RING_GROUPS = LRB_RING_GROUPS;
 constexpr int RING_REC_BYTES = 80;   // 16 fp32 + int32 gid0, padded to a multiple of 16 B
 
 // c-th largest score of an unsorted set (1 <= c <= 4); -inf if the set holds fewer than c entries.
@@ -387,6 +390,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   long long dbg_appends = 0, dbg_compactions = 0, dbg_tiles = 0, dbg_wait = 0, dbg_compact = 0, dbg_first = 0;
 #endif
 
+  // Programmatic dependent launch: the chunk launches of one lrb_score_topk call are independent (disjoint
+  // users, disjoint scratch), so the next chunk's CTAs may take over SMs as soon as CTAs of this launch
+  // exit instead of waiting for its slowest CTA.  (No-ops when launched without the attribute.)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -1024,6 +1031,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                              static_cast<unsigned long long>(dbg_tiles));
   }
 #endif
+  // ... but no launch may COMPLETE before its predecessor has: what follows the last chunk in the stream
+  // (the merge kernel) must see the results of every chunk.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   tc_fence_before();
   if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's tile halves / arrive on its barriers
   else __syncthreads();

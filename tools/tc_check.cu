@@ -35,6 +35,7 @@ extern "C" void lrb_debug_set_score_mode(int m);
 extern "C" void lrb_debug_set_stats(long long* p);
 extern "C" void lrb_debug_set_scout(int t);
 extern "C" void lrb_debug_set_pair_drain(int v);
+extern "C" void lrb_debug_set_overlap(int v);
 
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
@@ -358,6 +359,7 @@ int main(int argc, char** argv) {
     int mode = argc > 5 ? atoi(argv[5]) : 0;
     if (argc > 6 && atoi(argv[6]) >= 0) { lrb_debug_set_scout(atoi(argv[6])); printf("scout tiles %d\n", atoi(argv[6])); }
     if (argc > 7) { lrb_debug_set_pair_drain(atoi(argv[7])); printf("pair drain %d\n", atoi(argv[7])); }
+    if (argc > 8) { lrb_debug_set_overlap(atoi(argv[8])); printf("chunk overlap %d\n", atoi(argv[8])); }
     lrb_debug_set_score_mode(mode);
     if (mode) printf("debug mode %d\n", mode);
     time_topk(B, rows, K, true, true);
