@@ -199,11 +199,22 @@ def run_product(args, rank, world, local_rank):
     labels_dev = labels_host.to(device)
     ks = [1, 5, 10, 20]
 
+    shard = world
     if world > 1:
-        retr = ShardedRetriever(CudaBackend(model, rank, world, precision="bf16"), exchange=args.exchange)
+        # row-shard degree S: the table is split over S ranks and replicated world/S times (S = world by
+        # default: one copy of the table in the whole job, BASELINE.json configs[3])
+        shard = args.shard_degree or world
+        assert world % shard == 0 and (shard == world or weak), "--shard-degree must divide --gpus (weak scaling only)"
+        group, grank = None, rank
+        if shard != world:
+            for g in range(world // shard):
+                pg = dist.new_group(list(range(g * shard, (g + 1) * shard)))
+                if rank // shard == g:
+                    group, grank = pg, rank % shard
+        retr = ShardedRetriever(CudaBackend(model, grank, shard, precision="bf16"), group=group, exchange=args.exchange)
         fn = retr.retrieve_dp if weak else retr.retrieve
         step = lambda x: fn(x, k=TOPK, exclude_history=True, labels=labels_dev, ks=ks)
-        rows = shard_range(N_ITEMS + 1, rank, world)
+        rows = shard_range(N_ITEMS + 1, grank, shard)
         local_rows = rows[1] - rows[0]
     else:
         step = lambda x: model.retrieve(x, k=TOPK, exclude_history=True, labels=labels_dev, ks=ks, precision="bf16")
@@ -298,9 +309,11 @@ def run_product(args, rank, world, local_rank):
     global_batch = BATCH * world if weak else BATCH
     value = global_batch * args.steps / (ms_total * 1e-3)
     e2e_value = global_batch * args.steps / e2e_s
-    flops = 2.0 * global_batch * local_rows * 64                # algorithmic FLOPs of one rank's scoring call
+    scored_users = BATCH * shard if weak else BATCH             # users one rank scores against its rows
+    flops = 2.0 * scored_users * local_rows * 64                # algorithmic FLOPs of one rank's scoring call
     sms = torch.cuda.get_device_properties(device).multi_processor_count
-    score_launches = -(-global_batch // (128 * sms))            # one launch per chunk of 128 x SMs users
+    cap = (sms // 2 // 4) * 256                                 # users per scoring launch (score.cu: users_per_launch)
+    score_launches = -(-scored_users // cap) if scored_users > cap else 1
     achieved = flops / (score_ms_mean * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -316,7 +329,8 @@ def run_product(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "batch_per_gpu": BATCH if (weak or world == 1) else BATCH // world,
                    "global_batch": global_batch, "max_len": MAX_LEN, "k": TOPK,
-                   "parallelism": (f"item table row-sharded x{world}; users data-parallel ({BATCH} per GPU); user states "
+                   "parallelism": (f"item table row-sharded x{shard}" + (f" (replicated x{world // shard})" if shard != world else "")
+                                   + f"; users data-parallel ({BATCH} per GPU); user states "
                                    f"gathered and local top-{TOPK} lists scattered to their owners by "
                                    + ("the kernels' own stores into peer memory over NVLink" if retr._peer and all(
                                        v is not None for v in retr._peer.values()) else "NCCL all-gather / all-to-all")
@@ -355,6 +369,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--shard-degree", type=int, default=0,
+                    help="N > 1, weak scaling: ranks per copy of the item table (default N: one copy per job)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
                     help="N > 1, weak scaling: stores into peer memory (default when available) or NCCL collectives")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
