@@ -312,7 +312,7 @@ def run_product(args, rank, world, local_rank):
     scored_users = BATCH * shard if weak else BATCH             # users one rank scores against its rows
     flops = 2.0 * scored_users * local_rows * 64                # algorithmic FLOPs of one rank's scoring call
     sms = torch.cuda.get_device_properties(device).multi_processor_count
-    cap = (sms // 2 // 4) * 256                                 # users per scoring launch (score.cu: users_per_launch)
+    cap = (sms // 2 // 2) * 256                                 # users per scoring launch (score.cu: users_per_launch)
     score_launches = -(-scored_users // cap) if scored_users > cap else 1
     achieved = flops / (score_ms_mean * 1e-3) / 1e12
     traffic = None

@@ -11,6 +11,14 @@
 #include <cmath>
 #include <cstdlib>
 
+#ifdef LRB_DEBUG_MODES
+static int g_debug_cap_div = 0;
+extern "C" void lrb_debug_set_cap_div(int v) { g_debug_cap_div = v; }
+extern "C" void lrb_debug_set_greedy(int) {}
+#else
+static const int g_debug_cap_div = 0;
+#endif
+
 namespace lrb {
 
 // ============================================================================================
@@ -204,20 +212,19 @@ Decomp decompose(int B, long long rows, int units, int bm = tc::BM) {
   return d;
 }
 
-// Users per launch.  The kernel is at its best when every user is swept by >= 4 concurrent full streams:
-// the union bound (c <= 4 entries per stream) then filters from the first tiles on, and the remainder
-// ("shared") stream is a small part of the grid.  Larger batches (the all-gathered users of a
-// data-parallel job) are therefore processed as consecutive launches over equal user chunks
-// (measured on B200, 32768 users x 1.25M rows: one launch per 18944 users 7.7 ms, per 4096 users 6.8 ms).
+// Users per launch.  A streaming top-K restarts for every (launch, item range) and its start-up is the
+// expensive part (thresholds are weak until a few thousand items have been seen), so large batches -- the
+// all-gathered users of a data-parallel job -- want few, long segments; but the union bound needs
+// c * 2 * s_full >= K with c <= MAX_C_SHARE entries per stream, and a launch whose user tiles divide the SM
+// pairs evenly has no remainder ("shared") stream.  148 SMs: 37 pair tiles = 9472 users per launch, two full
+// streams per user, c = 5.  Measured on B200 (debug build, 32768 users x 1.25M rows): launches of 4096 users
+// 8.85 ms, 5632: 8.70, 8192: 8.39, 9472 (+ one of 4352): 8.30, 18944 (no union bound): 10.2.
 inline int users_per_launch(int B, int sms) {
   const int units = sms >= 2 ? sms / 2 : 1;                 // CTA pairs
-  int cap_tiles = units / 4;                                 // pair tiles (256 users) per launch
+  int cap_tiles = units / (g_debug_cap_div > 0 ? g_debug_cap_div : 2);   // pair tiles (256 users) per launch
   if (cap_tiles < 1) cap_tiles = 1;
   const int cap = cap_tiles * 2 * tc::BM;
-  if (B <= cap) return B;
-  const int n_chunks = (B + cap - 1) / cap;
-  const int per = (B + n_chunks - 1) / n_chunks;
-  return (per + 2 * tc::BM - 1) / (2 * tc::BM) * (2 * tc::BM);
+  return B <= cap ? B : cap;
 }
 
 // CTA pairs (tcgen05 cta_group::2) whenever a launch has more than one user tile: the pair shares every
@@ -483,7 +490,7 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     {
       // entries each of the 2*s_full full-stream threads of a user must hold for the union bound
       const int c = d.s_full > 0 ? (K + 2 * d.s_full - 1) / (2 * d.s_full) : 99;
-      p.c_share = c <= 4 ? c : 0;
+      p.c_share = c <= tc::MAX_C_SHARE ? c : 0;
       // scout pass: worth its T0 extra tiles when the union bound exists and segments are long enough
       const long long seg_tiles = d.s_full > 0 ? d.full_tiles / d.s_full : 0;
       p.scout_tiles = (p.c_share > 0 && seg_tiles >= 128) ? 16 : 0;

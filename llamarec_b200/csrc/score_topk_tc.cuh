@@ -51,7 +51,7 @@ struct ScoreParams {
                                // user all start at t = 0; with c * 2*s_full >= K the minimum over them is a
                                // valid lower bound on the user's K-th best (union bound), also used by the
                                // shared-stream CTAs, whose own slots are ignored (they may start late).
-  int c_share;                 // c (1..4); 0 disables the union bound
+  int c_share;                 // c (1..MAX_C_SHARE); 0 disables the union bound
   int pair_drain;              // CTA pairs: a drain request is forwarded to the peer CTA (1) or stays local (0)
   int scout_tiles;             // T0: the last T0 tiles of every segment are first run in "scout" mode (no
                                // candidate handling, only group maxima) to seed the union bound; 0 = off
@@ -230,20 +230,24 @@ __device__ __noinline__ float topk_consider(float s, int gid, int row_limit_gid,
 constexpr int RING_GROUPS = LRB_RING_GROUPS;
 constexpr int RING_REC_BYTES = 80;   // 16 fp32 + int32 gid0, padded to a multiple of 16 B
 
-// c-th largest score of an unsorted set (1 <= c <= 4); -inf if the set holds fewer than c entries.
+// c-th largest score of an unsorted set (1 <= c <= MAX_C_SHARE); -inf if the set holds fewer than c entries.
+constexpr int MAX_C_SHARE = 6;
 template <int STRIDE>
 LRB_DEVINL float set_cth_best(uint32_t ls, uint32_t ln, int c) {
   const int n = lds_s32(ln);
-  float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY;   // running top-4, descending
+  float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY, m5 = -INFINITY,
+        m6 = -INFINITY;   // running top-6, descending
   for (int i = 0; i < n; ++i) {
     float v = lds_f32(ls + i * STRIDE * 4);
     float t;
     t = fminf(m1, v); m1 = fmaxf(m1, v); v = t;
     t = fminf(m2, v); m2 = fmaxf(m2, v); v = t;
     t = fminf(m3, v); m3 = fmaxf(m3, v); v = t;
-    m4 = fmaxf(m4, v);
+    t = fminf(m4, v); m4 = fmaxf(m4, v); v = t;
+    t = fminf(m5, v); m5 = fmaxf(m5, v); v = t;
+    m6 = fmaxf(m6, v);
   }
-  return c == 1 ? m1 : (c == 2 ? m2 : (c == 3 ? m3 : m4));
+  return c == 1 ? m1 : (c == 2 ? m2 : (c == 3 ? m3 : (c == 4 ? m4 : (c == 5 ? m5 : m6))));
 }
 
 struct RingRec {
@@ -650,7 +654,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_scout = (kDense || p.scout_tiles <= 0 || p.c_share <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
       const int n_scout_run = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
       if (n_scout_run > 0) {
-        float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;   // descending
+        float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY, t4 = -INFINITY,
+              t5 = -INFINITY;   // descending
         for (int it = 0; it < n_scout_run; ++it) {
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tc_fence_after();
@@ -677,7 +682,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
               hi = fmaxf(t0, x); x = fminf(t0, x); t0 = hi;
               hi = fmaxf(t1, x); x = fminf(t1, x); t1 = hi;
               hi = fmaxf(t2, x); x = fminf(t2, x); t2 = hi;
-              t3 = fmaxf(t3, x);
+              hi = fmaxf(t3, x); x = fminf(t3, x); t3 = hi;
+              hi = fmaxf(t4, x); x = fminf(t4, x); t4 = hi;
+              t5 = fmaxf(t5, x);
             }
             if (c < 3) tmem_ld_wait();
           }
@@ -699,7 +706,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             E = lo2 - lo;
           }
           const int mth = p.c_share + E;   // 1-based rank of the group maximum that is safe to publish
-          const float cb = mth == 1 ? t0 : (mth == 2 ? t1 : (mth == 3 ? t2 : (mth == 4 ? t3 : -INFINITY)));
+          const float cb = mth == 1 ? t0 : (mth == 2 ? t1 : (mth == 3 ? t2 : (mth == 4 ? t3 : (mth == 5 ? t4 :
+                           (mth == 6 ? t5 : -INFINITY)))));
           if (cb > -INFINITY) {
             published = float_to_key(cb);
             p.gslots[static_cast<size_t>(b) * p.gstride + my_slot] = published;
