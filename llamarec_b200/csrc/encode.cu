@@ -168,7 +168,9 @@ struct InprojParams {
 
 constexpr int SMEM_INPROJ = (D * TOK + D * H2 + TOK * 65) * 4 + TOK * 4;
 
-__global__ void __launch_bounds__(THREADS, 1) embed_inproj_kernel(const InprojParams p) {
+// 97 KB of shared memory and <= 128 registers: two CTAs per SM (the id -> row gather is latency-bound and
+// wants the extra warps in flight).
+__global__ void __launch_bounds__(THREADS, 2) embed_inproj_kernel(const InprojParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* At = reinterpret_cast<float*>(smem_raw);   // [64][TOK]
   float* Ws = At + D * TOK;                          // [64][256]
@@ -518,7 +520,7 @@ int lrb_encode_fwd(const int64_t* ids, int B, int L, const float* table_f32, int
   LRB_CUDA_TRY(cudaFuncSetAttribute(outproj_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OUT));
   const int sms = device_sm_count();
   const int max_tiles = static_cast<int>((T + TOK - 1) / TOK);
-  const int grid_tok = max_tiles < sms ? max_tiles : sms;
+  const int grid_tok = max_tiles < 2 * sms ? max_tiles : 2 * sms;   // embed_inproj: two CTAs per SM
 
   float* x_cur = xa;    // output of the previous block / embedding
   float* x_nxt = xb;
