@@ -66,7 +66,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -230,7 +230,7 @@ def run_product(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("LRB_BENCH_NO_SAMPLER"):
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + (5 if world > 1 else 0)):   # + first-use set-up of the exchange buffers
         step(ids_dev)
     barrier()
     # keep the GPU under the same load until the sampler has produced its first rows
@@ -247,6 +247,11 @@ def run_product(args, rank, world, local_rank):
     barrier()
 
     # ---- device-resident timing (value) ----
+    # a host-side pause longer than the launch queue's slack stalls the GPU, and with N ranks in lock-step any
+    # rank's pause stalls all of them: keep the collector out of the timed regions
+    import gc
+    gc.collect()
+    gc.disable()
     model.profile_events = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -282,6 +287,7 @@ def run_product(args, rank, world, local_rank):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    gc.enable()
 
     if os.environ.get("LRB_BENCH_PHASES") and weak:
         # developer aid: per-phase GPU times of the data-parallel step (rank 0, stderr)
