@@ -5,6 +5,7 @@ from .model import LRURec, merge_lists  # noqa: F401
 from .metrics import absolute_recall_mrr_ndcg_for_ks, absolute_metrics_batch_wrapper  # noqa: F401
 from .retriever import LRURetriever  # noqa: F401
 from .verbalizer import ManualVerbalizer  # noqa: F401
+from . import stage2  # noqa: F401
 from .sharded import CudaBackend, ShardedRetriever, shard_range  # noqa: F401
 
 __all__ = ["LRURec", "merge_lists", "absolute_recall_mrr_ndcg_for_ks", "absolute_metrics_batch_wrapper",

@@ -171,6 +171,40 @@ def test_verbalizer_kernel_matches_reference():
         np.testing.assert_allclose(v.process_logits(torch.from_numpy(d["logits"])).numpy(), d[f"out_pls{pls}"], atol=1e-6)
 
 
+def test_stage2_caller_matches_full_lm_head_chain():
+    """score_candidates (transformer body -> last hidden state -> label-row kernel) against the reference chain
+    lm_head at every position -> .float() -> [:, -1] -> process_logits (model/llm.py:113-131, trainer/llm.py:63-72)
+    on a tiny random-init Llama; the metrics on the label scores match the metrics oracle."""
+    transformers = pytest.importorskip("transformers")
+    from llamarec_b200 import stage2
+
+    class Tok:   # 'A'..'T' -> fixed ids, like the fake tokenizer of oracle/make_golden.py
+        def encode(self, word, add_special_tokens=False):
+            return [100 + ord(word[-1]) - ord("A")]
+
+    cfg = transformers.LlamaConfig(vocab_size=1000, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                                   num_attention_heads=4, num_key_value_heads=4, max_position_embeddings=128)
+    torch.manual_seed(0)
+    llm = transformers.LlamaForCausalLM(cfg).to(torch.bfloat16).cuda().eval()
+    ids = torch.randint(5, 1000, (37, 23), device="cuda")
+    labels = torch.randint(0, 20, (37,), device="cuda")
+    for post in (False, True):
+        vb = ManualVerbalizer(tokenizer=Tok(), prefix="", post_log_softmax=post, classes=list(range(20)),
+                              label_words={i: chr(ord("A") + i) for i in range(20)})
+        got = stage2.score_candidates(llm, vb, ids)
+        with torch.no_grad():
+            logits = llm(input_ids=ids).logits.float()[:, -1]
+        ref = vb.process_logits(logits)
+        # both sides round the 20 logits to bf16 (fp32 accumulation order may move one of them by one bf16 ulp)
+        assert torch.allclose(got, ref, atol=2e-2, rtol=1e-2), (got - ref).abs().max()
+        # bf16-rounded logits can tie exactly; argsort's tie order is implementation-defined, so de-tie first
+        got = got - 1e-4 * torch.arange(20, device="cuda", dtype=torch.float32)
+        m = stage2.rerank_metrics(got, labels, [1, 5, 10])
+        m_ref = MO.recall_mrr_ndcg(got.cpu(), labels.cpu(), [1, 5, 10])
+        for k, v in m_ref.items():
+            assert abs(m[k] - v) < 5e-5, (k, m[k], v)
+
+
 # ------------------------------------------------------------------------------------------------
 # Larger shapes: oracle on the same seeded inputs (seconds on CPU) and size-independent properties
 # ------------------------------------------------------------------------------------------------
