@@ -132,6 +132,23 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
                     int64_t M, int64_t rows, int precision, float* out, int64_t ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Train-step forward loss without the logits tensor.
+ * Replaces, in value, LRUTrainer.calculate_loss (trainer/lru.py:22-28): `model(seqs).view(-1, N+1)`
+ * followed by nn.CrossEntropyLoss(ignore_index=0) (trainer/lru.py:20) -- an online log-sum-exp over
+ * the catalogue fused with the scoring contraction (exact fp32 path).
+ *   hidden [M][64] fp32: encoder output at every position (lrb_encode_fwd, all_positions = 1), M = B*L
+ *   table_f32 [rows][64], bias_pad: as for lrb_score_dense (rows = N+1, the whole table)
+ *   labels [M] int64; rows whose label == ignore_index do not count
+ * Outputs: row_loss [M] (optional, 0 for ignored rows); loss_sum[2] += {sum of row losses, counted
+ *   rows} (the caller zeroes it; mean loss = loss_sum[0] / loss_sum[1]).
+ * Workspace: lrb_ce_workspace_bytes(M, rows).
+ * ------------------------------------------------------------------------------------------ */
+size_t lrb_ce_workspace_bytes(int64_t M, int64_t rows);
+int lrb_ce_loss_fwd(const float* hidden, const float* table_f32, const float* bias_pad, int64_t M, int64_t rows,
+                    const int64_t* labels, int64_t ignore_index, float* row_loss, float* loss_sum,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * k-way merge + Recall/MRR/NDCG + candidate emission, one fused kernel.
  * Replaces absolute_recall_mrr_ndcg_for_ks (trainer/utils.py:43-90), the label membership test and
  * candidate list of LRUTrainer.generate_candidates (trainer/lru.py:82-88, 114-132).

@@ -201,6 +201,34 @@ class LRURec(nn.Module):
         out["u"] = u
         return out
 
+    @torch.no_grad()
+    def ce_loss(self, x: torch.Tensor, labels: torch.Tensor, ignore_index: int = 0,
+                return_row_loss: bool = False):
+        """Value of the train-step loss, `CrossEntropyLoss(ignore_index=0)(model(x).view(-1, N+1), labels.view(-1))`
+        (trainer/lru.py:20-28), without the [B*L, N+1] logits: encoder at every position -> online log-sum-exp
+        over the catalogue fused with the scoring contraction (lrb_ce_loss_fwd, exact fp32).  Forward value
+        only (the kernels have no backward yet); the encoder runs in eval mode (dropout is identity)."""
+        lib = _lib.load()
+        if self.row_begin != 0 or self.row_end != self.num_items + 1:
+            raise RuntimeError("ce_loss needs the whole item table on this device (no row shard)")
+        hidden = self.hidden_states(x)                              # [B, L, 64]
+        c = self._prepare()
+        dev = hidden.device
+        B, L, _ = hidden.shape
+        M, rows = B * L, self.num_items + 1
+        labels = labels.to(dev).reshape(-1).to(torch.int64).contiguous()
+        if labels.numel() != M:
+            raise ValueError(f"labels has {labels.numel()} entries, expected B*L = {M}")
+        ws_bytes = lib.lrb_ce_workspace_bytes(M, rows)
+        ws = self._buf(("ce_ws", M, rows), (ws_bytes,), torch.uint8, dev)
+        row_loss = torch.empty(M, dtype=torch.float32, device=dev) if return_row_loss else None
+        acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        _lib.check(lib.lrb_ce_loss_fwd(_lib.ptr(hidden), _lib.ptr(c["table_f32"]), _lib.ptr(c["bias_pad"]), M, rows,
+                                       _lib.ptr(labels), int(ignore_index), _lib.ptr(row_loss), _lib.ptr(acc),
+                                       _lib.ptr(ws), ws_bytes, _lib.stream_handle()))
+        loss = acc[0] / acc[1]                                       # nan when every label is ignored, like torch
+        return (loss, row_loss.view(B, L)) if return_row_loss else loss
+
     # ------------------------------------------------------------------ internals
     @staticmethod
     def _precision(precision: str, rows: int) -> int:

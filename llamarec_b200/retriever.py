@@ -29,6 +29,12 @@ class LRURetriever:
     def to_device(self, batch):
         return [x.to(self.device, non_blocking=True) for x in batch]
 
+    # ---- trainer/lru.py:22-28 -------------------------------------------------------------------
+    def calculate_loss(self, batch) -> torch.Tensor:
+        """Value of the training loss of one batch (forward only; see LRURec.ce_loss)."""
+        seqs, labels = batch
+        return self.model.ce_loss(seqs, labels)
+
     # ---- trainer/lru.py:30-42 -------------------------------------------------------------------
     def calculate_metrics(self, batch, exclude_history: bool = True) -> Dict[str, float]:
         """Batch-mean Recall/MRR/NDCG@ks, keys in the reference's order (k descending)."""

@@ -121,6 +121,12 @@ def forward_scores(ids: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tens
     return torch.matmul(hidden_states(ids, sd), sd["embedding.token.weight"].t()) + sd["model.bias"]
 
 
+def ce_loss(ids: torch.Tensor, labels: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """trainer/lru.py:20-28 in eval mode: CrossEntropyLoss(ignore_index=0) on the logits at every position."""
+    logits = forward_scores(ids, sd)
+    return torch.nn.functional.cross_entropy(logits.view(-1, logits.size(-1)), labels.view(-1), ignore_index=0)
+
+
 def last_scores(ids: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     """model(x)[:, -1, :] without materialising the other positions (bit-identical, SURVEY probe P4)."""
     return torch.matmul(encode(ids, sd), sd["embedding.token.weight"].t()) + sd["model.bias"]

@@ -209,5 +209,42 @@ def main():
     print("verbalizer ok")
 
 
+def make_ce_fixture():
+    """Train-step loss (trainer/lru.py:20-28) of the REFERENCE on the committed weights and id matrices:
+    `python oracle/make_golden.py ce` writes tests/golden/ce_case.npz without touching the other fixtures."""
+    config, RefLRURec, tutils, tlru, verb = import_reference()
+    from oracle import lru_oracle as O
+    N = 400
+    args = SimpleNamespace(num_items=N, bert_hidden_units=64, bert_num_blocks=2, bert_dropout=0.2,
+                           bert_attn_dropout=0.2)
+    d = np.load(os.path.join(OUT, "lru_weights_n400.npz"))
+    sd = {k: torch.from_numpy(d[k]) for k in d.files}
+    ref = RefLRURec(args)
+    ref.load_state_dict(sd)
+    ref.eval()                                                    # dropout off: the RNG cannot be parity-matched
+    fake = SimpleNamespace(model=ref, ce=torch.nn.CrossEntropyLoss(ignore_index=0))
+    out = {}
+    g = torch.Generator().manual_seed(1)
+    for name in ("left_l20", "holes_l37", "left_l200"):
+        ids = torch.from_numpy(np.load(os.path.join(OUT, f"lru_case_{name}.npz"))["ids"])
+        labels = torch.zeros_like(ids)
+        labels[:, :-1] = ids[:, 1:]                               # next-item targets (dataloader/lru.py:98-118)
+        labels[:, -1] = torch.randint(1, N + 1, (ids.shape[0],), generator=g)
+        labels[ids == 0] = 0                                      # padding positions are ignored
+        with torch.no_grad():
+            loss = tlru.LRUTrainer.calculate_loss(fake, (ids, labels))
+            rows = torch.nn.functional.cross_entropy(ref(ids).view(-1, N + 1), labels.view(-1), ignore_index=0,
+                                                     reduction="none").view(ids.shape)
+        assert abs(O.ce_loss(ids, labels, sd).item() - loss.item()) < 1e-6, name
+        out[f"{name}_labels"] = labels.numpy()
+        out[f"{name}_loss"] = np.array(loss.item(), dtype=np.float64)
+        out[f"{name}_row_loss"] = rows.numpy()
+        print("ce", name, loss.item())
+    np.savez(os.path.join(OUT, "ce_case.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ce":
+        make_ce_fixture()
+    else:
+        main()

@@ -171,6 +171,30 @@ def test_verbalizer_kernel_matches_reference():
         np.testing.assert_allclose(v.process_logits(torch.from_numpy(d["logits"])).numpy(), d[f"out_pls{pls}"], atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["left_l20", "holes_l37", "left_l200"])
+def test_train_step_loss_matches_reference_cross_entropy(model, golden_sd, name):
+    """Fused log-sum-exp loss (no logits tensor) against the reference's LRUTrainer.calculate_loss
+    (trainer/lru.py:20-28, fixture ce_case.npz); labels = the next item, 0 where the input is padding."""
+    ce = np.load(os.path.join(GOLDEN, "ce_case.npz"))             # the reference's own loss on these inputs
+    ids = torch.from_numpy(load_case(name)["ids"])
+    labels = torch.from_numpy(ce[f"{name}_labels"])
+    ref = float(ce[f"{name}_loss"])
+    assert abs(O.ce_loss(ids, labels, golden_sd).item() - ref) < 1e-6
+    loss, rows = model.ce_loss(ids.cuda(), labels.cuda(), return_row_loss=True)
+    assert abs(loss.item() - ref) <= 1e-5 * max(1.0, abs(ref)), (loss.item(), ref)
+    np.testing.assert_allclose(rows.cpu().numpy(), ce[f"{name}_row_loss"], atol=2e-5, rtol=1e-5)
+    # the retriever-level mirror of LRUTrainer.calculate_loss
+    retr = LRURetriever(_args(400), model)
+    assert abs(retr.calculate_loss((ids.cuda(), labels.cuda())).item() - ref) <= 1e-5 * max(1.0, abs(ref))
+
+
+def test_train_step_loss_all_labels_ignored_is_nan(model):
+    ids = torch.zeros(3, 20, dtype=torch.int64)
+    ids[:, -1] = 5
+    loss = model.ce_loss(ids.cuda(), torch.zeros_like(ids).cuda())
+    assert torch.isnan(loss)                                   # torch's CrossEntropyLoss gives nan as well
+
+
 def test_stage2_caller_matches_full_lm_head_chain():
     """score_candidates (transformer body -> last hidden state -> label-row kernel) against the reference chain
     lm_head at every position -> .float() -> [:, -1] -> process_logits (model/llm.py:113-131, trainer/llm.py:63-72)

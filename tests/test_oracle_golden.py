@@ -100,3 +100,13 @@ def test_verbalizer_oracle():
     ids2, tm2, wm2 = (torch.from_numpy(d[k]) for k in ("multi_label_words_ids", "multi_words_ids_mask",
                                                        "multi_label_words_mask"))
     np.testing.assert_allclose(VO.process_logits(logits, ids2, tm2, wm2, True).numpy(), d["multi_out"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["left_l20", "holes_l37", "left_l200"])
+def test_oracle_train_step_loss_matches_reference(golden_sd, name):
+    """oracle.ce_loss against LRUTrainer.calculate_loss of the reference itself (tests/golden/ce_case.npz,
+    written by `python oracle/make_golden.py ce`)."""
+    ce = np.load(os.path.join(GOLDEN, "ce_case.npz"))
+    ids = torch.from_numpy(load_case(name)["ids"])
+    labels = torch.from_numpy(ce[f"{name}_labels"])
+    assert abs(O.ce_loss(ids, labels, golden_sd).item() - float(ce[f"{name}_loss"])) < 1e-6
