@@ -349,7 +349,8 @@ def run_product(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": ids_pinned.numel() * 8 * (world if weak else 1),
                 "d2h_bytes_per_step": (BATCH * TOPK * 8 + len(ks) * 3 * 4) * (world if weak else 1)},
         # per step: prepare_sequences, 6 encoder kernels, scoring launch(es), local merge (+ final merge)
-        "gpu_launches": args.steps * (1 + 6 + score_launches + 1 + (1 if world > 1 else 0)),
+        # (+ the peer-push kernel of the data-parallel exchange; torch's barrier kernels are not counted)
+        "gpu_launches": args.steps * (1 + 6 + score_launches + 1 + (1 if world > 1 else 0) + (1 if weak else 0)),
         "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": achieved,
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,

@@ -6,6 +6,10 @@
 #include "api_util.h"
 #include "score_topk_tc.cuh"
 
+#ifndef LRB_NS_PAIR
+#define LRB_NS_PAIR 4   // TMA stages of the K <= 20 CTA-pair kernel (20 KB each)
+#endif
+
 #include <cuda.h>
 #include <climits>
 #include <cmath>
@@ -14,7 +18,6 @@
 #ifdef LRB_DEBUG_MODES
 static int g_debug_cap_div = 0;
 extern "C" void lrb_debug_set_cap_div(int v) { g_debug_cap_div = v; }
-extern "C" void lrb_debug_set_greedy(int) {}
 #else
 static const int g_debug_cap_div = 0;
 #endif
@@ -504,7 +507,7 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
     const bool ov = chunk_idx > 0 && g_debug_overlap;
     if (cg == 2) {
-      if (K <= 20) rc = launch_tc<20, 4, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
+      if (K <= 20) rc = launch_tc<20, LRB_NS_PAIR, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
       else if (K <= 32) rc = launch_tc<32, 4, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
       else rc = launch_tc<50, 3, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
     } else {

@@ -32,3 +32,6 @@ def test_size_queries_without_gpu():
     assert lib.lrb_encoder_weight_floats(2) == 128 + 2 * 66816
     assert lib.lrb_encode_workspace_bytes(16, 200, 0) >= 16 * 200 * (64 * 2 + 256) * 4
     assert isinstance(lib.lrb_last_error(), (bytes, type(None)))
+    # 9472 users per scoring launch on 148 SMs: the scratch grows with the number of chunk launches
+    assert lib.lrb_score_scratch_bytes(32768) > lib.lrb_score_scratch_bytes(4096) > 0
+    assert lib.lrb_ce_workspace_bytes(3200, 12087) >= 3200 * 3 * 4

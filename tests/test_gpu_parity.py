@@ -326,6 +326,41 @@ def test_data_parallel_exchange_records_on_one_device(games_model):
     assert torch.allclose(out["metric_sums"], ref_sums, rtol=1e-5)
 
 
+def test_peer_push_and_scatter_merge_with_local_destinations(games_model):
+    """The exchange kernels with every "peer" mapped to local memory: lrb_peer_push copies each array into its
+    slot of every destination; lrb_merge_metrics_scatter writes user b's list to row b % n of destination b / n
+    and equals the plain merge."""
+    from llamarec_b200 import _lib
+    lib = _lib.load()
+    m, sd, cfg = games_model
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    arrays = [torch.randn(96, 64, device=dev, generator=g).to(torch.bfloat16),
+              torch.randint(0, 1 << 30, (96, 52), device=dev, generator=g, dtype=torch.int32),
+              torch.randint(0, 1 << 30, (96, 4), device=dev, generator=g, dtype=torch.int32)]
+    n_dst, slot = 3, 1
+    dst = [[torch.zeros((4 * a.shape[0],) + tuple(a.shape[1:]), dtype=a.dtype, device=dev) for _ in range(n_dst)]
+           for a in arrays]
+    src = (_lib.ctypes.c_void_p * 3)(*[a.data_ptr() for a in arrays])
+    nbytes = (_lib.ctypes.c_size_t * 3)(*[a.numel() * a.element_size() for a in arrays])
+    ptrs = (_lib.ctypes.c_void_p * 9)(*[dst[a][d][slot * 96:].data_ptr() for a in range(3) for d in range(n_dst)])
+    _lib.check(lib.lrb_peer_push(src, nbytes, 3, ptrs, n_dst, _lib.stream_handle()))
+    for a in range(3):
+        for d in range(n_dst):
+            assert torch.equal(dst[a][d][slot * 96:(slot + 1) * 96], arrays[a])
+            assert not dst[a][d][:slot * 96].any() and not dst[a][d][(slot + 1) * 96:].any()
+    # scatter merge: 300 users, 2 destinations of 150 rows each, rows [2][k] interleaved
+    ids, _ = synth.make_sequences(cfg, num_users=300, seed=21)
+    part = m.retrieve(ids.cuda(), k=20, precision="bf16", merge=False)
+    plain = merge_lists(part["part_scores"], part["part_ids"], part["part_cnt"], k_out=20)
+    recv = [torch.full((150, 2, 20), -7, dtype=torch.int32, device=dev) for _ in range(2)]
+    scatter = {"dst_scores": [r.data_ptr() for r in recv], "dst_ids": [r.data_ptr() + 20 * 4 for r in recv],
+               "users_per_dst": 150, "out_stride": 40}
+    merge_lists(part["part_scores"], part["part_ids"], part["part_cnt"], k_out=20, scatter=scatter)
+    got = torch.cat(recv)
+    assert torch.equal(got[:, 0].view(torch.float32), plain["scores"]) and torch.equal(got[:, 1], plain["ids"])
+
+
 def test_full_size_10m_catalogue_properties():
     """BASELINE config 4 (10M items, batch 4096): properties that need no CPU pass over the table, plus an
     exact check of 4 users against a plain torch fp32 matmul over the same bf16 operands."""

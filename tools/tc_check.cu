@@ -37,7 +37,6 @@ extern "C" void lrb_debug_set_scout(int t);
 extern "C" void lrb_debug_set_pair_drain(int v);
 extern "C" void lrb_debug_set_overlap(int v);
 extern "C" void lrb_debug_set_cap_div(int v);
-extern "C" void lrb_debug_set_greedy(int v);
 
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
@@ -363,7 +362,6 @@ int main(int argc, char** argv) {
     if (argc > 7) { lrb_debug_set_pair_drain(atoi(argv[7])); printf("pair drain %d\n", atoi(argv[7])); }
     if (argc > 8) { lrb_debug_set_overlap(atoi(argv[8])); printf("chunk overlap %d\n", atoi(argv[8])); }
     if (argc > 9) { lrb_debug_set_cap_div(atoi(argv[9])); printf("streams per user >= %d\n", atoi(argv[9])); }
-    if (argc > 10) { lrb_debug_set_greedy(atoi(argv[10])); printf("greedy chunks %d\n", atoi(argv[10])); }
     lrb_debug_set_score_mode(mode);
     if (mode) printf("debug mode %d\n", mode);
     time_topk(B, rows, K, true, true);
