@@ -210,6 +210,14 @@ int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head_bf16, int 
                          const int32_t* word_ids, const uint8_t* word_mask, int C, int W, int mode,
                          int round_bf16, float* out, void* stream);
 
+/* ManualVerbalizer.process_logits on logits that already exist (trainer/verb.py:546-586, the call of
+ * trainer/llm.py:68 and demo/inference.py:68): logits [B][ld] fp32 (ld >= V), tok_ids/tok_mask
+ * [C][W][T] (sub-tokens of every label word), word_mask [C][W]; handler = handle_multi_token
+ * (trainer/verb.py:280-305): 0 first, 1 max, 2 mean; mode as above.  out [B][C]. */
+int lrb_verbalizer_from_logits(const float* logits, int64_t ld, int B, int64_t V, const int32_t* tok_ids,
+                               const uint8_t* tok_mask, const uint8_t* word_mask, int C, int W, int T,
+                               int handler, int mode, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,37 @@ LRB_DEVINL void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
   }
 }
 
+// Verbalizer post-processing for one user, executed by a whole warp (lanes = label words):
+//   project   : logit - 10000 * (1 - word_mask)                          trainer/verb.py:543
+//   normalize : softmax over ALL label words, log(p + 1e-15)   (mode 1)  trainer/verb.py:570-582
+//   aggregate : masked mean over the W words of each class               trainer/verb.py:611-614
+LRB_DEVINL void verbalizer_tail(int mode, int C, int W, const unsigned char* word_mask, float logit, int lane,
+                                float* out_row) {
+  const int n_words = C * W;
+  float x = -INFINITY;
+  float m = 0.f;
+  if (lane < n_words) {
+    m = word_mask[lane] ? 1.f : 0.f;
+    x = logit - 10000.0f * (1.0f - m);
+  }
+  if (mode == 1) {
+    float mx = x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = lane < n_words ? expf(x - mx) : 0.f;
+    const float den = warp_sum(e);
+    x = logf(e / den + 1e-15f);
+  }
+  const float num = lane < n_words ? x * m : 0.f;
+  float tot = 0.f, totm = 0.f;
+  for (int j = 0; j < W; ++j) {
+    const int src = (lane / W) * W + j;
+    tot += __shfl_sync(0xffffffffu, num, src & 31);
+    totm += __shfl_sync(0xffffffffu, m, src & 31);
+  }
+  if (lane < n_words && (lane % W) == 0) out_row[lane / W] = tot / totm;
+}
+
 template <int NVEC>   // NVEC = H / 256: 16-byte vectors per lane per row
 __global__ void __launch_bounds__(WARPS * 32) verbalizer_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -96,31 +127,59 @@ __global__ void __launch_bounds__(WARPS * 32) verbalizer_kernel(const Params p) 
   const int b = b0 + warp;
   if (b >= p.B) return;
 
-  // ---- verbalizer post-processing, one warp per user, lanes = label words ----
-  float x = -INFINITY;
-  float m = 0.f;
+  verbalizer_tail(p.mode, p.C, p.W, p.word_mask, lane < n_words ? s_logit[warp][lane] : 0.f, lane,
+                  p.out + static_cast<size_t>(b) * p.C);
+}
+
+// ---------------------------------------------------------------------------------------------
+// process_logits on precomputed logits [B][V] (the reference's own entry point, trainer/verb.py:546-586):
+// one warp per user, lanes = label words; the word's sub-token logits are gathered and reduced by the
+// multi_token_handler (first / max / mean, trainer/verb.py:280-305), then the same tail runs.
+// ---------------------------------------------------------------------------------------------
+struct LogitParams {
+  const float* logits;             // [B][V]
+  long long ld;                    // row pitch of logits (elements)
+  int B;
+  long long V;
+  const int* tok_ids;              // [C][W][T]
+  const unsigned char* tok_mask;   // [C][W][T]
+  const unsigned char* word_mask;  // [C][W]
+  int C, W, T, mode, handler;      // handler 0 = first, 1 = max, 2 = mean
+  float* out;                      // [B][C]
+};
+
+__global__ void __launch_bounds__(WARPS * 32) verbalizer_logits_kernel(const LogitParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WARPS + warp;
+  if (b >= p.B) return;
+  const int n_words = p.C * p.W;
+  float x = 0.f;
   if (lane < n_words) {
-    m = p.word_mask[lane] ? 1.f : 0.f;
-    x = s_logit[warp][lane] - 10000.0f * (1.0f - m);      // trainer/verb.py:543
+    const float* row = p.logits + static_cast<size_t>(b) * p.ld;
+    const int* ids = p.tok_ids + lane * p.T;
+    const unsigned char* tm = p.tok_mask + lane * p.T;
+    auto at = [&](int t) {
+      long long tok = ids[t];
+      if (tok < 0 || tok >= p.V) tok = 0;
+      return __ldg(row + tok);
+    };
+    if (p.handler == 0) {
+      x = at(0);
+    } else if (p.handler == 1) {
+      float mx = -INFINITY;
+      for (int t = 0; t < p.T; ++t) mx = fmaxf(mx, at(t) - 1000.0f * (1.0f - (tm[t] ? 1.f : 0.f)));
+      x = mx;
+    } else {
+      float sum = 0.f, cnt = 0.f;
+      for (int t = 0; t < p.T; ++t) {
+        const float m = tm[t] ? 1.f : 0.f;
+        sum += at(t) * m;
+        cnt += m;
+      }
+      x = sum / (cnt + 1e-15f);
+    }
   }
-  if (p.mode == 1) {
-    // softmax over ALL label words of all classes, then log(p + 1e-15)   (trainer/verb.py:570-582)
-    float mx = x;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float e = lane < n_words ? expf(x - mx) : 0.f;
-    const float den = warp_sum(e);
-    x = logf(e / den + 1e-15f);
-  }
-  // aggregate: masked mean over the W words of each class                   (trainer/verb.py:611-614)
-  const float num = lane < n_words ? x * m : 0.f;
-  float tot = 0.f, totm = 0.f;
-  for (int j = 0; j < p.W; ++j) {
-    const int src = (lane / p.W) * p.W + j;
-    tot += __shfl_sync(0xffffffffu, num, src & 31);
-    totm += __shfl_sync(0xffffffffu, m, src & 31);
-  }
-  if (lane < n_words && (lane % p.W) == 0) p.out[static_cast<size_t>(b) * p.C + lane / p.W] = tot / totm;
+  verbalizer_tail(p.mode, p.C, p.W, p.word_mask, x, lane, p.out + static_cast<size_t>(b) * p.C);
 }
 
 }  // namespace verb
@@ -165,6 +224,27 @@ extern "C" int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head
   else if (nvec == 32) LRB_VERB_LAUNCH(32);
   else return set_error(LRB_ERR_UNSUPPORTED, "hidden size %d is not one of the instantiated widths", H);
 #undef LRB_VERB_LAUNCH
+  LRB_CUDA_TRY(cudaGetLastError());
+  return LRB_OK;
+}
+
+extern "C" int lrb_verbalizer_from_logits(const float* logits, int64_t ld, int B, int64_t V, const int32_t* tok_ids,
+                                          const uint8_t* tok_mask, const uint8_t* word_mask, int C, int W, int T,
+                                          int handler, int mode, float* out, void* stream) {
+  using namespace lrb;
+  int rc = check_arch();
+  if (rc != LRB_OK) return rc;
+  LRB_REQUIRE(logits && tok_ids && tok_mask && word_mask && out, "lrb_verbalizer_from_logits: null pointer");
+  LRB_REQUIRE(B > 0 && V > 0 && C > 0 && W > 0 && T > 0 && ld >= V, "lrb_verbalizer_from_logits: bad shape");
+  LRB_REQUIRE(mode == 0 || mode == 1, "lrb_verbalizer_from_logits: mode must be 0 (raw) or 1 (log-softmax)");
+  LRB_REQUIRE(handler >= 0 && handler <= 2, "lrb_verbalizer_from_logits: handler is 0 first, 1 max, 2 mean");
+  if (C * W > verb::MAX_WORDS)
+    return set_error(LRB_ERR_UNSUPPORTED, "at most %d label words in total (got %d x %d)", verb::MAX_WORDS, C, W);
+  verb::LogitParams p;
+  p.logits = logits; p.ld = ld; p.B = B; p.V = V; p.tok_ids = tok_ids; p.tok_mask = tok_mask;
+  p.word_mask = word_mask; p.C = C; p.W = W; p.T = T; p.mode = mode; p.handler = handler; p.out = out;
+  const int grid = (B + verb::WARPS - 1) / verb::WARPS;
+  verb::verbalizer_logits_kernel<<<grid, verb::WARPS * 32, 0, as_stream(stream)>>>(p);
   LRB_CUDA_TRY(cudaGetLastError());
   return LRB_OK;
 }

@@ -1,7 +1,8 @@
 """Verbalizer with the reference's interface (trainer/verb.py:420-643, copy in demo/verb.py).
 
 `ManualVerbalizer(tokenizer, classes, label_words, prefix, multi_token_handler, post_log_softmax)` keeps
-the constructor and `process_logits(logits[B, V]) -> [B, C]`.  The fast path is
+the constructor and `process_logits(logits[B, V]) -> [B, C]` (project, handle_multi_token, normalize, log and
+aggregate of trainer/verb.py:524-614 in one kernel, lrb_verbalizer_from_logits).  The fast path is
 
     score_hidden(hidden_last[B, H], lm_head_weight[V, H]) -> [B, C]
 
@@ -110,26 +111,41 @@ class ManualVerbalizer:
                                             1 if round_logits_to_bf16 else 0, _lib.ptr(out), _lib.stream_handle()))
         return out
 
-    # ---- reference-compatible path on precomputed logits (trainer/verb.py:524-614) -----------------
-    def project(self, logits: torch.Tensor) -> torch.Tensor:
-        dev = logits.device
-        picked = logits[:, self.label_words_ids.to(dev)]                    # [B, C, W, T]
-        tok_mask = self.words_ids_mask.to(dev)
-        if self.multi_token_handler == "first":
-            picked = picked[..., 0]
-        elif self.multi_token_handler == "max":
-            picked = (picked - 1000 * (1 - tok_mask.unsqueeze(0))).max(dim=-1).values
-        elif self.multi_token_handler == "mean":
-            picked = (picked * tok_mask.unsqueeze(0)).sum(-1) / (tok_mask.unsqueeze(0).sum(-1) + 1e-15)
-        else:
-            raise ValueError(f"multi_token_handler {self.multi_token_handler} not configured")
-        return picked - 10000 * (1 - self.label_words_mask.to(dev))
+    # ---- the reference's entry point on precomputed logits (trainer/verb.py:524-614) ----------------
+    _HANDLERS = {"first": 0, "max": 1, "mean": 2}
 
     def process_logits(self, logits: torch.Tensor) -> torch.Tensor:
-        words = self.project(logits)
-        if self.post_log_softmax:
-            B = words.shape[0]
-            probs = torch.softmax(words.reshape(B, -1), dim=-1).reshape(words.shape)
-            words = torch.log(probs + 1e-15)
-        m = self.label_words_mask.to(words.device)
-        return (words * m).sum(-1) / m.sum(-1)
+        """trainer/verb.py:546-586.  CUDA logits run in lrb_verbalizer_from_logits (one kernel: gather the
+        label-word logits, multi-token handler, project, normalize/log, aggregate); host tensors -- the
+        reference's trainer hands over numpy logits (trainer/llm.py:65-68) -- are moved to the current CUDA
+        device first when there is one."""
+        if self.multi_token_handler not in self._HANDLERS:
+            raise ValueError(f"multi_token_handler {self.multi_token_handler} not configured")
+        if not logits.is_cuda and torch.cuda.is_available():
+            return self.process_logits(logits.cuda()).to(logits.device)
+        if logits.is_cuda:
+            lib = _lib.load()
+            dev = logits.device
+            lg = logits.to(torch.float32)
+            if lg.stride(-1) != 1:
+                lg = lg.contiguous()
+            ids, tmask, wmask = self._device_token_params(dev)
+            B, V = lg.shape
+            C, W, T = ids.shape
+            out = torch.empty(B, C, dtype=torch.float32, device=dev)
+            _lib.check(lib.lrb_verbalizer_from_logits(lg.data_ptr(), lg.stride(0), B, V, _lib.ptr(ids), _lib.ptr(tmask),
+                                                      _lib.ptr(wmask), C, W, T,
+                                                      self._HANDLERS[self.multi_token_handler],
+                                                      1 if self.post_log_softmax else 0, _lib.ptr(out),
+                                                      _lib.stream_handle()))
+            return out
+        raise RuntimeError("ManualVerbalizer.process_logits needs a CUDA device: project / normalize / aggregate "
+                           "(trainer/verb.py:524-614) run in one kernel, there is no CPU path")
+
+    def _device_token_params(self, dev):
+        key = ("tok", str(dev))
+        if key not in self._dev_cache:
+            self._dev_cache[key] = (self.label_words_ids.to(torch.int32).contiguous().to(dev),
+                                    self.words_ids_mask.to(torch.uint8).contiguous().to(dev),
+                                    self.label_words_mask.to(torch.uint8).contiguous().to(dev))
+        return self._dev_cache[key]

@@ -243,8 +243,37 @@ def make_ce_fixture():
     np.savez(os.path.join(OUT, "ce_case.npz"), **out)
 
 
+def make_verbalizer_handler_fixture():
+    """ManualVerbalizer.process_logits of the REFERENCE with multi_token_handler = max / mean on multi-token label
+    words: `python oracle/make_golden.py verb` writes tests/golden/verbalizer_handlers.npz."""
+    config, RefLRURec, tutils, tlru, verb = import_reference()
+    from oracle import verbalizer_oracle as VO
+
+    class Tok:
+        def encode(self, word, add_special_tokens=False):
+            return [17 + (ord(c) * 7) % 250 for c in word]
+    d = np.load(os.path.join(OUT, "verbalizer_case.npz"))
+    logits = torch.from_numpy(d["logits"])
+    classes = list(range(16))     # 16 classes x 2 words = 32 label words (the kernel's lanes)
+    lw = {i: ([chr(ord("A") + i), "xy" + chr(ord("a") + i)] if i % 4 else [chr(ord("A") + i) + "q"]) for i in range(16)}
+    out = {}
+    for handler in ("first", "max", "mean"):
+        for pls in (False, True):
+            rv = verb.ManualVerbalizer(tokenizer=Tok(), prefix="", post_log_softmax=pls, classes=classes,
+                                       label_words=lw, multi_token_handler=handler)
+            r = rv.process_logits(logits.clone())
+            o = VO.process_logits(logits, rv.label_words_ids.data, rv.words_ids_mask.data, rv.label_words_mask.data,
+                                  pls, handler)
+            assert torch.allclose(o, r, atol=1e-6), (handler, pls)
+            out[f"{handler}_pls{int(pls)}"] = r.detach().numpy()
+    np.savez(os.path.join(OUT, "verbalizer_handlers.npz"), **out)
+    print("verbalizer handlers ok")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "ce":
+    if len(sys.argv) > 1 and sys.argv[1] == "verb":
+        make_verbalizer_handler_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ce":
         make_ce_fixture()
     else:
         main()

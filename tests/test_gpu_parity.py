@@ -167,8 +167,23 @@ def test_verbalizer_kernel_matches_reference():
         lg = torch.nn.functional.linear(hid.float().cpu(), w.float().cpu())
         ref = v.process_logits(lg)
         np.testing.assert_allclose(exact.numpy(), ref.numpy(), atol=2e-4, rtol=RTOL)
-        # compat path on precomputed logits reproduces the reference outputs
-        np.testing.assert_allclose(v.process_logits(torch.from_numpy(d["logits"])).numpy(), d[f"out_pls{pls}"], atol=1e-6)
+        # process_logits on precomputed logits (lrb_verbalizer_from_logits) reproduces the reference outputs
+        np.testing.assert_allclose(v.process_logits(torch.from_numpy(d["logits"])).numpy(), d[f"out_pls{pls}"],
+                                   atol=5e-6, rtol=2e-6)
+    # multi-token label words, all three handlers, against the reference class (verbalizer_handlers.npz)
+    h = np.load(os.path.join(GOLDEN, "verbalizer_handlers.npz"))
+    lw = {i: ([chr(ord("A") + i), "xy" + chr(ord("a") + i)] if i % 4 else [chr(ord("A") + i) + "q"]) for i in range(16)}
+    logits = torch.from_numpy(d["logits"]).cuda()
+    for handler in ("first", "max", "mean"):
+        for pls in (0, 1):
+            v = ManualVerbalizer(Tok(), classes=list(range(16)), label_words=lw, prefix="",
+                                 post_log_softmax=bool(pls), multi_token_handler=handler)
+            got = v.process_logits(logits).cpu().numpy()
+            np.testing.assert_allclose(got, h[f"{handler}_pls{pls}"], atol=5e-6, rtol=2e-6)
+    # a non-contiguous view of a wider logits matrix (row pitch > V)
+    wide = torch.zeros(logits.shape[0], logits.shape[1] + 37, device="cuda")
+    wide[:, :logits.shape[1]] = logits
+    np.testing.assert_allclose(v.process_logits(wide[:, :logits.shape[1]]).cpu().numpy(), got, atol=1e-7)
 
 
 @pytest.mark.parametrize("name", ["left_l20", "holes_l37", "left_l200"])

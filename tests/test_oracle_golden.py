@@ -110,3 +110,23 @@ def test_oracle_train_step_loss_matches_reference(golden_sd, name):
     ids = torch.from_numpy(load_case(name)["ids"])
     labels = torch.from_numpy(ce[f"{name}_labels"])
     assert abs(O.ce_loss(ids, labels, golden_sd).item() - float(ce[f"{name}_loss"])) < 1e-6
+
+
+def test_oracle_multi_token_handlers_match_reference():
+    """first / max / mean handlers on multi-token label words against the reference class itself
+    (tests/golden/verbalizer_handlers.npz, written by `python oracle/make_golden.py verb`)."""
+    from llamarec_b200 import ManualVerbalizer
+
+    class Tok:
+        def encode(self, word, add_special_tokens=False):
+            return [17 + (ord(c) * 7) % 250 for c in word]
+    d = np.load(os.path.join(GOLDEN, "verbalizer_case.npz"))
+    h = np.load(os.path.join(GOLDEN, "verbalizer_handlers.npz"))
+    logits = torch.from_numpy(d["logits"])
+    lw = {i: ([chr(ord("A") + i), "xy" + chr(ord("a") + i)] if i % 4 else [chr(ord("A") + i) + "q"]) for i in range(16)}
+    for handler in ("first", "max", "mean"):
+        for pls in (0, 1):
+            v = ManualVerbalizer(Tok(), classes=list(range(16)), label_words=lw, prefix="",
+                                 post_log_softmax=bool(pls), multi_token_handler=handler)   # label-word tables only
+            o = VO.process_logits(logits, v.label_words_ids, v.words_ids_mask, v.label_words_mask, bool(pls), handler)
+            np.testing.assert_allclose(o.numpy(), h[f"{handler}_pls{pls}"], atol=1e-6)
