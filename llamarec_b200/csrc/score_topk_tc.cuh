@@ -231,23 +231,29 @@ constexpr int RING_GROUPS = LRB_RING_GROUPS;
 constexpr int RING_REC_BYTES = 80;   // 16 fp32 + int32 gid0, padded to a multiple of 16 B
 
 // c-th largest score of an unsorted set (1 <= c <= MAX_C_SHARE); -inf if the set holds fewer than c entries.
-constexpr int MAX_C_SHARE = 6;
+#ifndef LRB_MAX_C_SHARE
+#define LRB_MAX_C_SHARE 6
+#endif
+constexpr int MAX_C_SHARE = LRB_MAX_C_SHARE;
 template <int STRIDE>
 LRB_DEVINL float set_cth_best(uint32_t ls, uint32_t ln, int c) {
   const int n = lds_s32(ln);
-  float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY, m5 = -INFINITY,
-        m6 = -INFINITY;   // running top-6, descending
+  float m[MAX_C_SHARE];   // running top-MAX_C_SHARE, descending
+#pragma unroll
+  for (int j = 0; j < MAX_C_SHARE; ++j) m[j] = -INFINITY;
   for (int i = 0; i < n; ++i) {
     float v = lds_f32(ls + i * STRIDE * 4);
-    float t;
-    t = fminf(m1, v); m1 = fmaxf(m1, v); v = t;
-    t = fminf(m2, v); m2 = fmaxf(m2, v); v = t;
-    t = fminf(m3, v); m3 = fmaxf(m3, v); v = t;
-    t = fminf(m4, v); m4 = fmaxf(m4, v); v = t;
-    t = fminf(m5, v); m5 = fmaxf(m5, v); v = t;
-    m6 = fmaxf(m6, v);
+#pragma unroll
+    for (int j = 0; j < MAX_C_SHARE; ++j) {
+      const float t = fminf(m[j], v);
+      m[j] = fmaxf(m[j], v);
+      v = t;
+    }
   }
-  return c == 1 ? m1 : (c == 2 ? m2 : (c == 3 ? m3 : (c == 4 ? m4 : (c == 5 ? m5 : m6))));
+  float r = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < MAX_C_SHARE; ++j) r = (c == j + 1) ? m[j] : r;
+  return r;
 }
 
 struct RingRec {
@@ -654,8 +660,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_scout = (kDense || p.scout_tiles <= 0 || p.c_share <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
       const int n_scout_run = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
       if (n_scout_run > 0) {
-        float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY, t4 = -INFINITY,
-              t5 = -INFINITY;   // descending
+        float tm[MAX_C_SHARE];   // the MAX_C_SHARE largest group maxima, descending
+#pragma unroll
+        for (int j = 0; j < MAX_C_SHARE; ++j) tm[j] = -INFINITY;
         for (int it = 0; it < n_scout_run; ++it) {
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tc_fence_after();
@@ -678,13 +685,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const float m4 = max3(q[9], q[10], q[11]);
               const float m5 = max3(q[12], q[13], q[14]);
               float x = fmaxf(max3(m1, m2, m3), max3(m4, m5, q[15]));
-              float hi;
-              hi = fmaxf(t0, x); x = fminf(t0, x); t0 = hi;
-              hi = fmaxf(t1, x); x = fminf(t1, x); t1 = hi;
-              hi = fmaxf(t2, x); x = fminf(t2, x); t2 = hi;
-              hi = fmaxf(t3, x); x = fminf(t3, x); t3 = hi;
-              hi = fmaxf(t4, x); x = fminf(t4, x); t4 = hi;
-              t5 = fmaxf(t5, x);
+#pragma unroll
+              for (int j = 0; j < MAX_C_SHARE; ++j) {
+                const float hi = fmaxf(tm[j], x);
+                x = fminf(tm[j], x);
+                tm[j] = hi;
+              }
             }
             if (c < 3) tmem_ld_wait();
           }
@@ -706,8 +712,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             E = lo2 - lo;
           }
           const int mth = p.c_share + E;   // 1-based rank of the group maximum that is safe to publish
-          const float cb = mth == 1 ? t0 : (mth == 2 ? t1 : (mth == 3 ? t2 : (mth == 4 ? t3 : (mth == 5 ? t4 :
-                           (mth == 6 ? t5 : -INFINITY)))));
+          float cb = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < MAX_C_SHARE; ++j) cb = (mth == j + 1) ? tm[j] : cb;
           if (cb > -INFINITY) {
             published = float_to_key(cb);
             p.gslots[static_cast<size_t>(b) * p.gstride + my_slot] = published;
