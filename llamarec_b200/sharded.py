@@ -157,6 +157,7 @@ class PeerExchange:
             self.recv_off.append(off)
             off += al(world * b * 2 * k * 4)
         self.total = off
+        self.parity = 0     # which copy of the buffers the next step uses (all ranks step together)
         self.buf = symm.empty(self.total, dtype=torch.uint8, device=device)
         name = (group if group is not None else dist.group.WORLD).group_name
         self.hdl = symm.rendezvous(self.buf, name)
@@ -186,7 +187,6 @@ class ShardedRetriever:
             raise ValueError(f"unknown exchange {exchange!r}")
         self.exchange = exchange
         self._peer = {}
-        self._parity = 0
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._bufs = {}
@@ -230,8 +230,8 @@ class ShardedRetriever:
         from . import _lib
         lib = _lib.load()
         mark = self._mark
-        par = self._parity
-        self._parity ^= 1
+        par = px.parity
+        px.parity ^= 1
         arrays = [t for t in (st["state"], st["excl"], st["bloom"]) if t is not None]
         n_arr, R = len(arrays), self.world
         # 1. all-gather by stores: my b records go to slot `rank` of every rank's gather region
