@@ -51,61 +51,84 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md, the clocks line).
 
-    def __init__(self, index: int):
+    NVML is read in-process (pynvml; the same counters `nvidia-smi --query-gpu=clocks.sm,...` prints) from a
+    thread that only samples between activate() and stop(): the bench enqueues its K timed steps first and
+    activates the sampler while the GPU works through them.  An `nvidia-smi -lms` loop running while the host
+    is still launching was seen to stall the launch path (driver lock) for ~100 ms in 3 of 9 multi-GPU runs,
+    and with N ranks in lock-step one stalled rank stalls all of them."""
+
+    NAMES = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+             ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+             ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+             ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+
+    def __init__(self, index: int, period_s: float = 0.01):
         self.rows = []
-        self.proc = None
-        self.index = index
-        self.t_begin = None
-        self.t_end = None
+        self.period = period_s
+        self.active = False
+        self.done = False
+        self.nv = None
+        self.handle = None
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:   # honours CUDA_VISIBLE_DEVICES: look the device up by the UUID torch reports
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception as e:   # no NVML: the line says so instead of inventing clocks
+            self.error = repr(e)
+
+    def _read(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        return mhz, mask
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+        if self.nv is None:
+            return
+        def loop():
+            while not self.done:
+                if self.active:
+                    try:
+                        self.rows.append((time.time(),) + self._read())
+                    except Exception:
+                        pass
+                time.sleep(self.period)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
-
-    def mark_begin(self):
-        self.t_begin = time.time()
-
-    def mark_end(self):
-        self.t_end = time.time()
+    def activate(self):
+        if self.nv is not None:
+            try:   # one reading right away, so that even a region of a few ms has a sample
+                self.rows.append((time.time(),) + self._read())
+            except Exception:
+                pass
+        self.active = True
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        # samples inside the timed region; if the region is shorter than the sampling period, the
-        # samples taken under the same load just before it (warm-up) are used and flagged
-        inside = [r for (t, r) in self.rows if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t)]
-        window = "timed region"
-        if not inside:
-            inside = [r for (t, r) in self.rows if self.t_begin is None or t >= self.t_begin - 1.0]
-            window = "timed region + preceding 1 s of warm-up (region shorter than the sampling period)"
-        for r in inside:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+        self.active = False
+        self.done = True
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "error", "?")]}
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        sm = [r[1] for r in self.rows]
+        reasons = set()
+        for _, _, mask in self.rows:
+            for name, attr in self.NAMES:
+                if mask & int(getattr(self.nv, attr)):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region (NVML, sampled while the GPU executes the enqueued steps)"}
 
 
 def model_args(n_items):
@@ -226,24 +249,12 @@ def run_product(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one sampler (rank 0's GPU) is enough and keeps driver polling away from the other ranks
+    # one sampler (rank 0's GPU) is enough
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("LRB_BENCH_NO_SAMPLER"):
         sampler.start()
     for _ in range(max(args.warmup, 3) + (5 if world > 1 else 0)):   # + first-use set-up of the exchange buffers
         step(ids_dev)
-    barrier()
-    # keep the GPU under the same load until the sampler has produced its first rows
-    # (the continue/stop decision is agreed between the ranks: step() contains collectives)
-    t_spin = time.time()
-    while True:
-        step(ids_dev)
-        waiting = rank == 0 and sampler.proc is not None and len(sampler.rows) < 2 and time.time() - t_spin < 2.0
-        more = torch.tensor([1 if waiting else 0], device=device)
-        if world > 1:
-            dist.all_reduce(more, op=dist.ReduceOp.MAX)
-        if int(more.item()) == 0:
-            break
     barrier()
 
     # ---- device-resident timing (value) ----
@@ -253,17 +264,17 @@ def run_product(args, rank, world, local_rank):
     gc.collect()
     gc.disable()
     model.profile_events = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    sampler.mark_begin()
-    ev0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         out = step(ids_dev)
-    ev1.record()
+        marks[i + 1].record()
+    sampler.activate()          # everything is enqueued: sample clocks while the GPU works through it
     barrier()
-    sampler.mark_end()
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = marks[0].elapsed_time(marks[-1])
+    step_ms = [a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:])]
     score_ms = [a.elapsed_time(b) for a, b in model.profile_events]
     model.profile_events = None
 
@@ -330,7 +341,8 @@ def run_product(args, rank, world, local_rank):
             traffic = None
     line = {
         "metric": "users_per_sec_encode_score_top20", "value": value, "unit": "users/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "ms_per_step_median": statistics.median(step_ms), "ms_per_step_max": max(step_ms), "higher_is_better": True,
         "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "catalogue": N_ITEMS, "batch": BATCH, "batch_per_gpu": BATCH if (weak or world == 1) else BATCH // world,
