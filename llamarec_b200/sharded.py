@@ -212,6 +212,8 @@ class ShardedRetriever:
             return None
         if self.exchange == "auto" and not (dist.is_initialized() and dist.get_backend(self.group) == "nccl"):
             return None
+        if self.exchange == "auto" and self.world > 16:      # lrb_peer_push / scatter address <= 16 destinations
+            return None
         arrays = [t for t in (st["state"], st["excl"], st["bloom"]) if t is not None]
         rec = tuple(t[0].numel() * t.element_size() for t in arrays)
         key = (b, k, rec, str(arrays[0].dtype))

@@ -35,3 +35,18 @@ def test_size_queries_without_gpu():
     # 9472 users per scoring launch on 148 SMs: the scratch grows with the number of chunk launches
     assert lib.lrb_score_scratch_bytes(32768) > lib.lrb_score_scratch_bytes(4096) > 0
     assert lib.lrb_ce_workspace_bytes(3200, 12087) >= 3200 * 3 * 4
+
+
+def test_scoring_decomposition_without_gpu():
+    """Host-side work decomposition of the scoring kernel (148 SMs assumed when no device is present): 74 CTA
+    pairs; 4096 users = 16 pair tiles -> 4 full streams + a remainder stream = 12 partial lists per user;
+    9472 users = 37 pair tiles -> 2 full streams, no remainder; larger batches take the maximum over their chunks."""
+    lib = _lib.load()
+    s = ctypes.c_int(0)
+    for B, rows, want in ((4096, 10_000_001, 12), (9472, 1_250_001, 4), (32768, 1_250_001, 12), (100, 1683, None)):
+        assert lib.lrb_score_topk_slots(B, rows, 0, ctypes.byref(s)) == 0
+        assert s.value >= 2 and s.value % 2 == 0
+        if want is not None:
+            assert s.value == want, (B, rows, s.value)
+    assert lib.lrb_score_topk_slots(0, 10, 0, ctypes.byref(s)) != 0          # bad shape is an error, not a crash
+    assert b"bad arguments" in lib.lrb_last_error()
