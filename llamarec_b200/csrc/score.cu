@@ -470,6 +470,7 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
   // every chunk's union-bound slots are reset up front: nothing but kernels between the chunk launches
   LRB_CUDA_TRY(cudaMemsetAsync(scratch, 0x80, n_chunks * gs_chunk, st));
   int chunk_idx = 0;
+  int prev_ctas = 0;
   for (int c0 = 0; c0 < B; c0 += cap, ++chunk_idx) {
     // one launch per user chunk (see users_per_launch); chunk-relative pointers
     const int Bc = B - c0 < cap ? B - c0 : cap;
@@ -505,7 +506,11 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     p.slots = slots;
     p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
     p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
-    const bool ov = chunk_idx > 0 && g_debug_overlap;
+    // Overlap with the previous chunk launch is safe for the scratch as long as chunk i never runs next to
+    // chunk i-2 (they share a ring copy): one CTA fits per SM, so that cannot happen when chunk i-1 fills
+    // every SM -- chunk i can then only start once chunk i-2 is gone.
+    const bool ov = g_debug_overlap && (chunk_idx == 1 || (chunk_idx > 1 && prev_ctas >= sms));
+    prev_ctas = d.grid * cg;
     if (cg == 2) {
       if (K <= 20) rc = launch_tc<20, LRB_NS_PAIR, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
       else if (K <= 32) rc = launch_tc<32, 4, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
