@@ -266,6 +266,15 @@ def run_product(args, rank, world, local_rank):
     model.profile_events = []
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    # Let the host get ahead of the GPU before the timed steps start: a short spin kernel holds the stream while
+    # the K steps are enqueued behind it, so they run back to back from a full launch queue.  Without it the
+    # first steps are launched just in time, and a host-side pause on ANY rank (seen: one 15 ms step in a
+    # 20-step run at N = 4, median 5.9 ms) stalls every rank of the lock-step exchange.  The spin is outside the
+    # timed interval (marks[0] is recorded after it in stream order).
+    try:
+        torch.cuda._sleep(int(1.9e6 * min(100.0, 10.0 + 1.5 * args.steps)))
+    except Exception:
+        pass
     marks[0].record()
     for i in range(args.steps):
         out = step(ids_dev)
