@@ -10,10 +10,14 @@
 //         16-score group to a ring; rings are drained warp-wide (lock-step) into per-thread top-K sets.
 // The B x N score matrix never leaves the SM.
 //
-// Tile: 128 users (TMEM lanes) x 256 items (TMEM columns) x K=64; two TMEM accumulator stages.
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 = builds the "ones" block, warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4)..,
-// column half (w-4)/4).  The bias is folded into the GEMM as a fifth K=16 MMA per tile.
+// Tile: 128 users (TMEM lanes) x 256 items (TMEM columns) x K=64 per CTA; two TMEM accumulator stages.
+// CG = 2 (every launch with more than one user tile): two CTAs of a TPC form a pair (cluster of 2,
+// tcgen05 cta_group::2) that shares each 256-item tile -- every CTA stages only its 128 item rows, the leader
+// issues M = 256 MMAs, both CTAs read their own 128 x 256 accumulators out of their own TMEM.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM
+// allocator, warp 3 = builds the "ones" block, then threshold service (union bound), warps 4..11 = epilogue
+// (warp w reads TMEM lanes 32*(w%4).., column half (w-4)/4).  The bias is folded into the GEMM as a fifth
+// K=16 MMA per tile.  Consecutive launches of one call (user chunks) overlap via programmatic dependent launch.
 #pragma once
 
 #include <cuda.h>
