@@ -211,3 +211,60 @@ def test_sharded_retrieval_two_ranks_gloo(golden_sd):
     np.testing.assert_allclose(u, O.encode(x, golden_sd).numpy(), atol=1e-6)
     assert np.array_equal(i, ref_i.numpy().astype(np.int32))
     np.testing.assert_allclose(s, ref_s.numpy(), atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# Invariants behind the scoring kernel's threshold sharing, checked on the CPU:
+# whatever the kernel prunes with these bounds can never belong to a user's exact top-K.
+# ------------------------------------------------------------------------------------------------
+def _kth_best(values, k):
+    v = np.sort(np.asarray(values))[::-1]
+    return v[k - 1] if len(v) >= k else -np.inf
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_union_bound_never_exceeds_the_kth_best(seed):
+    """Every full-stream thread publishes the c-th best admissible score it has seen so far; with c * S >= K the
+    minimum over a user's S streams is a lower bound on the user's K-th best admissible score (ties included,
+    so filtering with `>=` keeps every top-K element)."""
+    rng = np.random.default_rng(seed)
+    for _ in range(200):
+        K = int(rng.integers(1, 51))
+        S = int(rng.choice([2, 4, 8, 12]))
+        c = -(-K // S)
+        n = int(rng.integers(S * c, 400))
+        scores = rng.integers(-5, 6, size=n).astype(np.float64)          # few distinct values: ties everywhere
+        excluded = rng.random(n) < 0.1
+        stream = rng.integers(0, S, size=n)
+        seen = rng.random(n) < rng.uniform(0.2, 1.0)                       # each stream is somewhere in its sweep
+        published = []
+        for s in range(S):
+            mine = scores[(stream == s) & seen & ~excluded]
+            published.append(_kth_best(mine, c))
+        bound = min(published)
+        if bound == -np.inf:
+            continue                                                       # undefined bound: nothing is pruned
+        kth = _kth_best(scores[~excluded], K)
+        assert kth >= bound
+        # hence every element of the exact top-K passes the `>= bound` filter
+        order = np.argsort(-scores[~excluded], kind="stable")[:K]
+        assert np.all(scores[~excluded][order] >= bound)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_scout_bound_accounts_for_excluded_ids(seed):
+    """The scout pass only sees the maxima of 16-item groups and does not look at ids; publishing the (c+E)-th
+    largest group maximum, E = excluded ids inside the scouted range, still leaves >= c admissible items at or
+    above the published value (the c+E maxima belong to c+E distinct items, at most E of them excluded)."""
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(200):
+        c = int(rng.integers(1, 7))
+        groups = int(rng.integers(8, 64))
+        scores = rng.integers(-3, 4, size=(groups, 16)).astype(np.float64)
+        excluded = rng.random((groups, 16)) < 0.05
+        E = int(excluded.sum())
+        gmax = np.sort(scores.max(axis=1))[::-1]
+        if c + E > len(gmax):
+            continue
+        published = gmax[c + E - 1]
+        assert int(((scores >= published) & ~excluded).sum()) >= c
