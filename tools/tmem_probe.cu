@@ -1,0 +1,141 @@
+// Developer micro-benchmark (not part of the product path): how fast can the accumulators of a K = 64 GEMM be read
+// out of TMEM while the next MMAs run?  DESIGN.md section 4.1 / 9: ~440 of the ~1260 cycles the scoring kernel
+// spends per 128 x 256 tile are tcgen05.ld time that does not overlap the MMA.  This probe times, per SM,
+//   mode 0: MMAs only (4 x M128 N256 K16 per tile, operands resident in shared memory)
+//   mode 1: + every accumulator read as fp32   (4 x tcgen05.ld.32x32b.x32 per epilogue warp)
+//   mode 2: + fp16 accumulators read packed    (2 x tcgen05.ld.32x32b.x32.pack::16b per epilogue warp)
+//   mode 3: loads of mode 1 without MMAs, mode 4: loads of mode 2 without MMAs
+// build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I llamarec_b200/csrc -o tools/tmem_probe tools/tmem_probe.cu
+// run:    tools/tmem_probe [tiles per SM]
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace lrb;
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 128 + EPI_WARPS * 32;
+constexpr int ACC = 2;
+
+LRB_DEVINL void tmem_ld_32x32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;                        // [128][64] bf16, 128-byte swizzle atoms (contents irrelevant)
+  uint8_t* sB = smem + BM * BK * 2;          // [256][64] bf16
+  __shared__ uint64_t full_bar[ACC], empty_bar[ACC];
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool mma_on = mode <= 2;
+  const int ld_mode = mode == 0 ? 0 : ((mode == 1 || mode == 3) ? 1 : 2);
+  for (int i = threadIdx.x; i < (BM + BN) * BK * 2 / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ACC; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == 2) { tmem_alloc(&tmem_ptr, ACC * BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  const long long t0 = clock64();
+  if (warp == 1 && lane == 0) {
+    uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (ld_mode == 2) idesc &= ~(3u << 4);                 // c_format = F16 accumulators
+    const uint64_t da = umma_desc_k_sw128(smem_u32(sA)), db = umma_desc_k_sw128(smem_u32(sB));
+    int acc = 0; uint32_t ph = 0;
+    for (int t = 0; t < tiles; ++t) {
+      mbar_wait(&empty_bar[acc], ph ^ 1);
+      tc_fence_after();
+      if (mma_on) {
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(tmem_base + acc * BN, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : 0u);
+      }
+      umma_commit(&full_bar[acc]);
+      if (++acc == ACC) { acc = 0; ph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4, quad = ew & 3, half = ew >> 2;
+    int acc = 0; uint32_t ph = 0;
+    unsigned x = 0;
+    for (int t = 0; t < tiles; ++t) {
+      mbar_wait(&full_bar[acc], ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * (BN / 2));
+      if (ld_mode == 1) {
+        uint32_t v[2][32];
+        tmem_ld_32x32(taddr, v[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < 3) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x ^= v[c & 1][j];
+          if (c < 3) tmem_ld_wait();
+        }
+      } else if (ld_mode == 2) {
+        uint32_t v[2][32];
+        tmem_ld_32x32_pack16(taddr, v[0]);           // 64 columns -> 32 registers
+        tmem_ld_32x32_pack16(taddr + 64, v[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x ^= v[0][j] ^ v[1][j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[acc]);
+      if (++acc == ACC) { acc = 0; ph ^= 1; }
+    }
+    if (x == 0x12345678u) sink[0] = x;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, ACC * BN); }
+}
+
+int main(int argc, char** argv) {
+  const int tiles = argc > 1 ? atoi(argv[1]) : 4000;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  long long* d_cycles; unsigned* d_sink;
+  cudaMalloc(&d_cycles, sms * sizeof(long long));
+  cudaMalloc(&d_sink, 4);
+  const int smem = (BM + BN) * BK * 2 + 1024;
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const char* names[5] = {"MMA only", "MMA + fp32 read-out", "MMA(f16 acc) + packed 16-bit read-out", "fp32 read-out only",
+                          "packed 16-bit read-out only"};
+  for (int mode = 0; mode < 5; ++mode) {
+    for (int rep = 0; rep < 2; ++rep) {
+      probe_kernel<<<sms, THREADS, smem>>>(tiles, mode, d_cycles, d_sink);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
+    }
+    std::vector<long long> h(sms);
+    cudaMemcpy(h.data(), d_cycles, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    double mean = 0;
+    for (long long c : h) mean += c;
+    mean /= sms;
+    printf("mode %d (%s): %.0f cycles per 128x256x64 tile per SM\n", mode, names[mode], mean / tiles);
+  }
+  return 0;
+}
