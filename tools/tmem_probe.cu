@@ -5,6 +5,10 @@
 //   mode 1: + every accumulator read as fp32   (4 x tcgen05.ld.32x32b.x32 per epilogue warp)
 //   mode 2: + fp16 accumulators read packed    (2 x tcgen05.ld.32x32b.x32.pack::16b per epilogue warp)
 //   mode 3: loads of mode 1 without MMAs, mode 4: loads of mode 2 without MMAs
+//   mode 5: mode 1 + the scoring kernel's filter per 32 columns (FMNMX3 max tree + one compare), 8 epilogue warps
+//   mode 6: the same with 16 epilogue warps (4 per SM sub-partition, 64 columns per thread)
+// Measured on B200 (round 1, 3000 tiles per SM, 1965 MHz): mode 0 = 520, mode 1 = 623 cycles per tile; mode 2 raised
+// "illegal instruction" (f16 accumulators and/or .pack::16b in this form) -- it only runs when asked for (argv[2]).
 // build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I llamarec_b200/csrc -o tools/tmem_probe tools/tmem_probe.cu
 // run:    tools/tmem_probe [tiles per SM]
 #include <cuda_runtime.h>
@@ -18,9 +22,9 @@
 using namespace lrb;
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 128 + EPI_WARPS * 32;
 constexpr int ACC = 2;
+
+LRB_DEVINL float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 LRB_DEVINL void tmem_ld_32x32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -36,7 +40,13 @@ LRB_DEVINL void tmem_ld_32x32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1) probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink) {
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(128 + EPI_WARPS * 32, 1)
+probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) {
+  constexpr int THREADS = 128 + EPI_WARPS * 32;
+  constexpr int PARTS = EPI_WARPS / 4;          // column parts per lane quadrant
+  constexpr int COLS = BN / PARTS;              // columns per epilogue thread
+  constexpr int CHUNKS = COLS / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;                        // [128][64] bf16, 128-byte swizzle atoms (contents irrelevant)
@@ -44,8 +54,9 @@ __global__ void __launch_bounds__(THREADS, 1) probe_kernel(int tiles, int mode, 
   __shared__ uint64_t full_bar[ACC], empty_bar[ACC];
   __shared__ uint32_t tmem_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool mma_on = mode <= 2;
-  const int ld_mode = mode == 0 ? 0 : ((mode == 1 || mode == 3) ? 1 : 2);
+  const bool mma_on = mode <= 2 || mode >= 5;
+  const int ld_mode = mode == 0 ? 0 : ((mode == 1 || mode == 3 || mode >= 5) ? 1 : 2);
+  const bool filter = mode >= 5;
   for (int i = threadIdx.x; i < (BM + BN) * BK * 2 / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (threadIdx.x == 0) {
@@ -77,20 +88,35 @@ __global__ void __launch_bounds__(THREADS, 1) probe_kernel(int tiles, int mode, 
     const int ew = warp - 4, quad = ew & 3, half = ew >> 2;
     int acc = 0; uint32_t ph = 0;
     unsigned x = 0;
+    int hits = 0;
     for (int t = 0; t < tiles; ++t) {
       mbar_wait(&full_bar[acc], ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * (BN / 2));
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * COLS);
       if (ld_mode == 1) {
         uint32_t v[2][32];
         tmem_ld_32x32(taddr, v[0]);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < 3) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        for (int c = 0; c < CHUNKS; ++c) {
+          if (c < CHUNKS - 1) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+          if (filter) {
+            // the scoring kernel's hot path: group maxima of 2 x 16 scores, one compare per 32 columns
+            float gm[2];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x ^= v[c & 1][j];
-          if (c < 3) tmem_ld_wait();
+            for (int g = 0; g < 2; ++g) {
+              float q[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(v[c & 1][g * 16 + j]);
+              gm[g] = fmaxf(max3f(max3f(q[0], q[1], q[2]), max3f(q[3], q[4], q[5]), max3f(q[6], q[7], q[8])),
+                            max3f(max3f(q[9], q[10], q[11]), max3f(q[12], q[13], q[14]), q[15]));
+            }
+            if (fmaxf(gm[0], gm[1]) >= thr) ++hits;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x ^= v[c & 1][j];
+          }
+          if (c < CHUNKS - 1) tmem_ld_wait();
         }
       } else if (ld_mode == 2) {
         uint32_t v[2][32];
@@ -105,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1) probe_kernel(int tiles, int mode, 
       if (lane == 0) mbar_arrive(&empty_bar[acc]);
       if (++acc == ACC) { acc = 0; ph ^= 1; }
     }
-    if (x == 0x12345678u) sink[0] = x;
+    if (x == 0x12345678u || hits == 0x7fffffff) sink[0] = x + hits;
   }
   tc_fence_before();
   __syncthreads();
@@ -113,29 +139,39 @@ __global__ void __launch_bounds__(THREADS, 1) probe_kernel(int tiles, int mode, 
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, ACC * BN); }
 }
 
+template <int EPI_WARPS>
+static double run(int sms, int tiles, int mode, long long* d_cycles, unsigned* d_sink) {
+  const int smem = (BM + BN) * BK * 2 + 1024;
+  cudaFuncSetAttribute(probe_kernel<EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) {
+    probe_kernel<EPI_WARPS><<<sms, 128 + EPI_WARPS * 32, smem>>>(tiles, mode, d_cycles, d_sink, 1e30f);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); exit(1); }
+  }
+  std::vector<long long> h(sms);
+  cudaMemcpy(h.data(), d_cycles, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+  double mean = 0;
+  for (long long c : h) mean += c;
+  return mean / sms / tiles;
+}
+
 int main(int argc, char** argv) {
   const int tiles = argc > 1 ? atoi(argv[1]) : 4000;
+  const bool try_f16 = argc > 2;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   long long* d_cycles; unsigned* d_sink;
   cudaMalloc(&d_cycles, sms * sizeof(long long));
   cudaMalloc(&d_sink, 4);
-  const int smem = (BM + BN) * BK * 2 + 1024;
-  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const char* names[5] = {"MMA only", "MMA + fp32 read-out", "MMA(f16 acc) + packed 16-bit read-out", "fp32 read-out only",
-                          "packed 16-bit read-out only"};
-  for (int mode = 0; mode < 5; ++mode) {
-    for (int rep = 0; rep < 2; ++rep) {
-      probe_kernel<<<sms, THREADS, smem>>>(tiles, mode, d_cycles, d_sink);
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
-    }
-    std::vector<long long> h(sms);
-    cudaMemcpy(h.data(), d_cycles, sms * sizeof(long long), cudaMemcpyDeviceToHost);
-    double mean = 0;
-    for (long long c : h) mean += c;
-    mean /= sms;
-    printf("mode %d (%s): %.0f cycles per 128x256x64 tile per SM\n", mode, names[mode], mean / tiles);
+  const char* names[7] = {"MMA only", "MMA + fp32 read-out", "MMA(f16 acc) + packed 16-bit read-out", "fp32 read-out only",
+                          "packed 16-bit read-out only", "MMA + fp32 read-out + max-tree filter, 8 epilogue warps",
+                          "MMA + fp32 read-out + max-tree filter, 16 epilogue warps"};
+  const int order[7] = {0, 1, 3, 5, 6, 2, 4};
+  for (int i = 0; i < 7; ++i) {
+    const int mode = order[i];
+    if ((mode == 2 || mode == 4) && !try_f16) continue;
+    const double cyc = mode == 6 ? run<16>(sms, tiles, mode, d_cycles, d_sink) : run<8>(sms, tiles, mode, d_cycles, d_sink);
+    printf("mode %d (%s): %.0f cycles per 128x256x64 tile per SM\n", mode, names[mode], cyc);
   }
   return 0;
 }
