@@ -6,7 +6,8 @@ from .metrics import absolute_recall_mrr_ndcg_for_ks, absolute_metrics_batch_wra
 from .retriever import LRURetriever  # noqa: F401
 from .verbalizer import ManualVerbalizer  # noqa: F401
 from . import stage2  # noqa: F401
+from .evalset import DeviceEvalSet  # noqa: F401
 from .sharded import CudaBackend, ShardedRetriever, shard_range  # noqa: F401
 
 __all__ = ["LRURec", "merge_lists", "absolute_recall_mrr_ndcg_for_ks", "absolute_metrics_batch_wrapper",
-           "LRURetriever", "ManualVerbalizer", "CudaBackend", "ShardedRetriever", "shard_range"]
+           "LRURetriever", "ManualVerbalizer", "CudaBackend", "ShardedRetriever", "shard_range", "DeviceEvalSet"]

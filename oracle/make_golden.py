@@ -270,8 +270,39 @@ def make_verbalizer_handler_fixture():
     print("verbalizer handlers ok")
 
 
+def make_evalset_fixture():
+    """LRUValidDataset / LRUTestDataset of the REFERENCE (dataloader/lru.py:129-180) on random user histories:
+    `python oracle/make_golden.py evalset` writes tests/golden/evalset_case.npz."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("ref_dataloader_lru", os.path.join(REF, "dataloader", "lru.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(11)
+    max_len = 12
+    train, val, test = {}, {}, {}
+    for u in rng.permutation(np.arange(1, 41)).tolist():              # unsorted insertion order on purpose
+        n = int(rng.integers(0, 30))
+        train[u] = rng.integers(1, 500, size=n).tolist()
+        val[u] = [int(rng.integers(1, 500))] if rng.random() < 0.85 else []
+        test[u] = [int(rng.integers(1, 500))] if rng.random() < 0.85 else []
+    dv = mod.LRUValidDataset(None, train, val, max_len, None)
+    dt = mod.LRUTestDataset(None, train, val, test, max_len, None)
+    out = {"max_len": np.array(max_len)}
+    for name, ds in (("val", dv), ("test", dt)):
+        items = [ds[i] for i in range(len(ds))]
+        out[f"{name}_seqs"] = torch.stack([a for a, _ in items]).numpy()
+        out[f"{name}_labels"] = torch.stack([b for _, b in items]).numpy()
+        out[f"{name}_users"] = np.array(ds.users)
+    out["dicts_json"] = np.array(json.dumps({"train": train, "val": val, "test": test}))
+    np.savez(os.path.join(OUT, "evalset_case.npz"), **out)
+    print("evalset ok", len(dv), len(dt))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "verb":
+    if len(sys.argv) > 1 and sys.argv[1] == "evalset":
+        make_evalset_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "verb":
         make_verbalizer_handler_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "ce":
         make_ce_fixture()

@@ -268,3 +268,28 @@ def test_scout_bound_accounts_for_excluded_ids(seed):
             continue
         published = gmax[c + E - 1]
         assert int(((scores >= published) & ~excluded).sum()) >= c
+
+
+def test_device_eval_set_matches_reference_datasets():
+    """DeviceEvalSet against LRUValidDataset / LRUTestDataset of the reference itself (dataloader/lru.py:129-180;
+    fixture evalset_case.npz from `python oracle/make_golden.py evalset`): same users in the same order, same
+    left-padded histories and labels, same batch boundaries as a shuffle=False DataLoader."""
+    import json
+    from llamarec_b200.evalset import DeviceEvalSet
+    d = np.load(os.path.join(ROOT, "tests", "golden", "evalset_case.npz"))
+    dicts = {k: {int(u): v for u, v in m.items()} for k, m in json.loads(str(d["dicts_json"])).items()}
+    L = int(d["max_len"])
+    val = DeviceEvalSet(dicts["train"], dicts["val"], L, batch_size=16, device="cpu")
+    test = DeviceEvalSet(dicts["train"], dicts["test"], L, batch_size=16, u2val=dicts["val"], device="cpu")
+    for name, ds in (("val", val), ("test", test)):
+        assert ds.users == d[f"{name}_users"].tolist()
+        assert ds.seqs.dtype == torch.int32 and ds.labels.dtype == torch.int64
+        assert np.array_equal(ds.seqs.numpy().astype(np.int64), d[f"{name}_seqs"])
+        assert np.array_equal(ds.labels.numpy(), d[f"{name}_labels"].reshape(-1))
+        batches = list(ds)
+        assert len(batches) == len(ds) == -(-len(ds.users) // 16)
+        assert torch.equal(torch.cat([b[0] for b in batches]), ds.seqs)
+        assert all(b[1].shape == (b[0].shape[0], 1) for b in batches)
+        assert ds.id_bytes()["int32_device"] * 2 == ds.id_bytes()["int64_reference"]
+    sub = DeviceEvalSet(dicts["train"], dicts["test"], L, 8, u2val=dicts["val"], device="cpu", subset_users=test.users[:5])
+    assert torch.equal(sub.seqs, test.seqs[:5])
