@@ -7,6 +7,8 @@
 //   mode 3: loads of mode 1 without MMAs, mode 4: loads of mode 2 without MMAs
 //   mode 5: mode 1 + the scoring kernel's filter per 32 columns (FMNMX3 max tree + one compare), 8 epilogue warps
 //   mode 6: the same with 16 epilogue warps (4 per SM sub-partition, 64 columns per thread)
+//   mode 7: 8 epilogue warps, loads double-buffered in PAIRS of 32-column chunks (128 load registers per thread,
+//           setmaxnreg: producer/MMA warpgroup down to 40 registers, epilogue warpgroups up to 232)
 // Measured on B200 (round 1, 3000 tiles per SM, 1965 MHz): mode 0 = 520, mode 1 = 623 cycles per tile; mode 2 raised
 // "illegal instruction" (f16 accumulators and/or .pack::16b in this form) -- it only runs when asked for (argv[2]).
 // build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I llamarec_b200/csrc -o tools/tmem_probe tools/tmem_probe.cu
@@ -40,7 +42,7 @@ LRB_DEVINL void tmem_ld_32x32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-template <int EPI_WARPS>
+template <int EPI_WARPS, bool PAIRBUF>
 __global__ void __launch_bounds__(128 + EPI_WARPS * 32, 1)
 probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) {
   constexpr int THREADS = 128 + EPI_WARPS * 32;
@@ -55,7 +57,7 @@ probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) 
   __shared__ uint32_t tmem_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool mma_on = mode <= 2 || mode >= 5;
-  const int ld_mode = mode == 0 ? 0 : ((mode == 1 || mode == 3 || mode >= 5) ? 1 : 2);
+  const int ld_mode = mode == 0 ? 0 : (PAIRBUF ? 3 : ((mode == 1 || mode == 3 || mode >= 5) ? 1 : 2));
   const bool filter = mode >= 5;
   for (int i = threadIdx.x; i < (BM + BN) * BK * 2 / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -68,6 +70,10 @@ probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_ptr;
+  if (PAIRBUF) {   // uniform per warpgroup (warps 0-3 | 4-7 | 8-11)
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  }
   const long long t0 = clock64();
   if (warp == 1 && lane == 0) {
     uint32_t idesc = umma_idesc_bf16(BM, BN);
@@ -118,6 +124,31 @@ probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) 
           }
           if (c < CHUNKS - 1) tmem_ld_wait();
         }
+      } else if (PAIRBUF && ld_mode == 3) {
+        // 4 chunks as two pairs: the second pair is in flight while the first is filtered
+        uint32_t a0[32], a1[32], b0[32], b1[32];
+        tmem_ld_32x32(taddr, a0);
+        tmem_ld_32x32(taddr + 32, a1);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 64, b0);
+        tmem_ld_32x32(taddr + 96, b1);
+        auto filt = [&](const uint32_t (&v)[32]) {
+          float gm[2];
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(v[g * 16 + j]);
+            gm[g] = fmaxf(max3f(max3f(q[0], q[1], q[2]), max3f(q[3], q[4], q[5]), max3f(q[6], q[7], q[8])),
+                          max3f(max3f(q[9], q[10], q[11]), max3f(q[12], q[13], q[14]), q[15]));
+          }
+          if (fmaxf(gm[0], gm[1]) >= thr) ++hits;
+        };
+        filt(a0);
+        filt(a1);
+        tmem_ld_wait();
+        filt(b0);
+        filt(b1);
       } else if (ld_mode == 2) {
         uint32_t v[2][32];
         tmem_ld_32x32_pack16(taddr, v[0]);           // 64 columns -> 32 registers
@@ -139,12 +170,12 @@ probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) 
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, ACC * BN); }
 }
 
-template <int EPI_WARPS>
+template <int EPI_WARPS, bool PAIRBUF = false>
 static double run(int sms, int tiles, int mode, long long* d_cycles, unsigned* d_sink) {
   const int smem = (BM + BN) * BK * 2 + 1024;
-  cudaFuncSetAttribute(probe_kernel<EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe_kernel<EPI_WARPS, PAIRBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int rep = 0; rep < 2; ++rep) {
-    probe_kernel<EPI_WARPS><<<sms, 128 + EPI_WARPS * 32, smem>>>(tiles, mode, d_cycles, d_sink, 1e30f);
+    probe_kernel<EPI_WARPS, PAIRBUF><<<sms, 128 + EPI_WARPS * 32, smem>>>(tiles, mode, d_cycles, d_sink, 1e30f);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); exit(1); }
   }
@@ -163,14 +194,17 @@ int main(int argc, char** argv) {
   long long* d_cycles; unsigned* d_sink;
   cudaMalloc(&d_cycles, sms * sizeof(long long));
   cudaMalloc(&d_sink, 4);
-  const char* names[7] = {"MMA only", "MMA + fp32 read-out", "MMA(f16 acc) + packed 16-bit read-out", "fp32 read-out only",
+  const char* names[8] = {"MMA only", "MMA + fp32 read-out", "MMA(f16 acc) + packed 16-bit read-out", "fp32 read-out only",
                           "packed 16-bit read-out only", "MMA + fp32 read-out + max-tree filter, 8 epilogue warps",
-                          "MMA + fp32 read-out + max-tree filter, 16 epilogue warps"};
-  const int order[7] = {0, 1, 3, 5, 6, 2, 4};
-  for (int i = 0; i < 7; ++i) {
+                          "MMA + fp32 read-out + max-tree filter, 16 epilogue warps",
+                          "MMA + fp32 read-out + max-tree filter, 8 warps, pair-buffered loads (setmaxnreg)"};
+  const int order[8] = {0, 1, 3, 5, 6, 7, 2, 4};
+  for (int i = 0; i < 8; ++i) {
     const int mode = order[i];
     if ((mode == 2 || mode == 4) && !try_f16) continue;
-    const double cyc = mode == 6 ? run<16>(sms, tiles, mode, d_cycles, d_sink) : run<8>(sms, tiles, mode, d_cycles, d_sink);
+    const double cyc = mode == 6 ? run<16>(sms, tiles, mode, d_cycles, d_sink)
+                     : mode == 7 ? run<8, true>(sms, tiles, mode, d_cycles, d_sink)
+                                 : run<8>(sms, tiles, mode, d_cycles, d_sink);
     printf("mode %d (%s): %.0f cycles per 128x256x64 tile per SM\n", mode, names[mode], cyc);
   }
   return 0;
