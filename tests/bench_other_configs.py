@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Times BASELINE.json configs 0-2 and 4 (the parity-test configurations, not the headline bench line) on one
-GPU, with the CPU oracle port beside each, and writes profiles/other_configs_rNN.json.  Developer tool."""
+GPU, with the CPU oracle port beside each, and writes gpurun_out/other_configs.json (copied to
+profiles/other_configs_rNN.json).  It lives under tests/ because it uses the oracle as its checker (the oracle is test
+infrastructure); it is not collected by pytest.  Run: python tests/bench_other_configs.py"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import torch
 from types import SimpleNamespace
 from llamarec_b200 import LRURec, LRURetriever, ManualVerbalizer, synth
