@@ -67,7 +67,8 @@ int lrb_prepare_table(const float* table_f32, const float* bias_f32, int64_t row
  * Sequence preparation: one pass over the id matrix.
  * Replaces LRUEmbedding.get_mask (model/lru.py:54-55), the power-of-two left pad
  * (model/lru.py:75-78) and the history mask of trainer/lru.py:36-38 (as a sorted exclusion list).
- *   ids        [B][L] int64, 0 = padding (dataloader/lru.py:147-149 left-pads)
+ *   ids        [B][L] int64 (the reference's LongTensors) or int32 (pre-padded device eval sets),
+ *              id_bytes = 8 or 4; 0 = padding (dataloader/lru.py:147-149 left-pads)
  *   all_positions = 0: eval mode, tokens before the first non-zero id are skipped
  *                 = 1: every position is a token (forward() at all L positions)
  * Outputs
@@ -78,7 +79,7 @@ int lrb_prepare_table(const float* table_f32, const float* bias_f32, int64_t row
  *   excl_bloom [B][4] 128-bit filter over (id & 127).  NULL iff excl_sorted is NULL.
  * ------------------------------------------------------------------------------------------ */
 int lrb_excl_stride(int L);
-int lrb_prepare_sequences(const int64_t* ids, int B, int L, int all_positions,
+int lrb_prepare_sequences(const void* ids, int id_bytes, int B, int L, int all_positions,
                           int32_t* tok_first, int32_t* tok_offset, int32_t* excl_sorted,
                           uint32_t* excl_bloom, void* stream);
 
@@ -89,6 +90,7 @@ int lrb_prepare_sequences(const int64_t* ids, int B, int L, int all_positions,
  * `weights` is the packed fp32 parameter blob described by lrb_encoder_weight_floats() /
  * llamarec_b200/packing.py (embedding LayerNorm, then per block: lambda re/im, gamma, W_in^T,
  * b_in, W_out^T (real part form), b_out, LN, W1^T, b1, W2^T, b2, LN).
+ *   ids / id_bytes: the id matrix handed to lrb_prepare_sequences (int64 or int32, consumed as is)
  *   table_f32 [N+1][64] fp32 embedding table (gathered by id)
  *   all_positions = 0: u[B][64] = hidden state at the last position (eval / retrieval)
  *                 = 1: hidden[B][L][64] at every position (train-step forward)
@@ -97,7 +99,7 @@ int lrb_prepare_sequences(const int64_t* ids, int B, int L, int all_positions,
  * ------------------------------------------------------------------------------------------ */
 size_t lrb_encoder_weight_floats(int n_blocks);
 size_t lrb_encode_workspace_bytes(int B, int L, int all_positions);
-int lrb_encode_fwd(const int64_t* ids, int B, int L, const float* table_f32, int64_t table_rows,
+int lrb_encode_fwd(const void* ids, int id_bytes, int B, int L, const float* table_f32, int64_t table_rows,
                    const float* weights, int n_blocks, int all_positions,
                    const int32_t* tok_first, const int32_t* tok_offset, float* out_f32,
                    void* out_bf16, void* workspace, size_t workspace_bytes, void* stream);

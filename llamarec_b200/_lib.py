@@ -22,10 +22,11 @@ SIGNATURES = {
     "lrb_bias_blk_bytes": (c_size_t, [c_int64]),
     "lrb_prepare_table": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lrb_excl_stride": (c_int, [c_int]),
-    "lrb_prepare_sequences": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lrb_prepare_sequences": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     "lrb_encoder_weight_floats": (c_size_t, [c_int]),
     "lrb_encode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "lrb_encode_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p,
+    "lrb_encode_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lrb_score_topk_slots": (c_int, [c_int, c_int64, c_int, POINTER(c_int)]),
     "lrb_score_scratch_bytes": (c_size_t, [c_int]),
@@ -91,6 +92,26 @@ def ptr(t) -> int | None:
     return t.data_ptr()
 
 
-def stream_handle() -> int | None:
+def stream_handle(device=None) -> int | None:
+    """Handle of torch's current stream on `device` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream or None
+    return torch.cuda.current_stream(device).cuda_stream or None
+
+
+class on_device:
+    """Context manager: makes the device that owns `tensor` current for the enclosed C-ABI calls (the kernels
+    launch on the current device's stream; pointers of another device would fault or go through peer access)."""
+
+    def __init__(self, tensor_or_device):
+        import torch
+        dev = tensor_or_device.device if hasattr(tensor_or_device, "device") else torch.device(tensor_or_device)
+        if dev.type != "cuda":
+            raise RuntimeError("llamarec_b200 has no CPU path: tensors must live on a CUDA device")
+        self._guard = torch.cuda.device(dev)
+
+    def __enter__(self):
+        self._guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self._guard.__exit__(*exc)

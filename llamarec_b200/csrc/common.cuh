@@ -295,11 +295,23 @@ LRB_DEVINL int lds_s32(uint32_t addr) {
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+// re-read on every call (another warp may have raised the value), but a plain LDS -- not a generic LD
+LRB_DEVINL int lds_volatile_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 LRB_DEVINL void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 LRB_DEVINL void sts_s32(uint32_t addr, int v) {
   asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Item ids come as int64 (the reference's LongTensors) or int32 (DeviceEvalSet): `id_bytes` is 8 or 4.
+LRB_DEVINL long long load_id(const void* __restrict__ ids, size_t idx, int id_bytes) {
+  return id_bytes == 4 ? static_cast<long long>(__ldg(static_cast<const int*>(ids) + idx))
+                       : __ldg(static_cast<const long long*>(ids) + idx);
 }
 
 LRB_DEVINL float warp_sum(float v) {

@@ -152,7 +152,8 @@ LRB_DEVINL void transpose_rows_to_kmajor(const float* Cs, float* At, int tid) {
 // Kernel 1: (embedding gather + LayerNorm | load x) -> in_proj -> * gamma -> bu[T][256]
 // =============================================================================================
 struct InprojParams {
-  const long long* ids;      // [B][L]
+  const void* ids;           // [B][L] int64 or int32
+  int id_bytes;              // 8 or 4
   const float* table;        // [rows][64]
   long long table_rows;
   const float* wts;          // packed blob
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 2) embed_inproj_kernel(const InprojPa
         if (i < T) {
           const int b = user_of_token(p.tok_offset, p.B, i);
           const int t = __ldg(p.tok_first + b) + (i - __ldg(p.tok_offset + b));
-          long long id = p.ids[static_cast<size_t>(b) * p.L + t];
+          long long id = load_id(p.ids, static_cast<size_t>(b) * p.L + t, p.id_bytes);
           if (id < 0 || id >= p.table_rows) id = 0;   // out-of-range ids are clamped to the pad row
           const float* row = p.table + static_cast<size_t>(id) * D;
           v0 = __ldg(row + lane);
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(THREADS, 2) embed_inproj_kernel(const InprojPa
 // =============================================================================================
 struct ScanParams {
   float2* bu;                // [T][128] complex, overwritten with h (unless last_only)
-  const long long* ids;      // [B][L]
+  const void* ids;           // [B][L] int64 or int32
+  int id_bytes;
   const float* wts;
   int blk;
   const int* tok_first;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(128) lru_scan_kernel(const ScanParams p) {
   const int base = __ldg(p.tok_offset + b);
   const int n = __ldg(p.tok_offset + b + 1) - base;
   const int off = (1 << p.levels) - p.L;   // left pad of the power-of-two frame
-  for (int t = c; t < p.L; t += 128) s_mask[t] = p.ids[static_cast<size_t>(b) * p.L + t] > 0 ? 1 : 0;
+  for (int t = c; t < p.L; t += 128) s_mask[t] = load_id(p.ids, static_cast<size_t>(b) * p.L + t, p.id_bytes) > 0 ? 1 : 0;
   __syncthreads();
   const float* blkw = p.wts + OFF_BLOCKS + static_cast<size_t>(p.blk) * BLOCK_FLOATS;
   const float lr = __ldg(blkw + B_LAM_RE + c), li = __ldg(blkw + B_LAM_IM + c);
@@ -490,7 +492,7 @@ size_t lrb_encode_workspace_bytes(int B, int L, int all_positions) {
   return 2 * align256(T * D * 4) + align256(T * H2 * 4) + align256(static_cast<size_t>(B) * H2 * 4);
 }
 
-int lrb_encode_fwd(const int64_t* ids, int B, int L, const float* table_f32, int64_t table_rows,
+int lrb_encode_fwd(const void* ids, int id_bytes, int B, int L, const float* table_f32, int64_t table_rows,
                    const float* weights, int n_blocks, int all_positions, const int32_t* tok_first,
                    const int32_t* tok_offset, float* out_f32, void* out_bf16, void* workspace,
                    size_t workspace_bytes, void* stream) {
@@ -501,6 +503,7 @@ int lrb_encode_fwd(const int64_t* ids, int B, int L, const float* table_f32, int
   LRB_REQUIRE(ids && table_f32 && weights && tok_first && tok_offset && out_f32 && workspace,
               "lrb_encode_fwd: null pointer");
   LRB_REQUIRE(B > 0 && L > 0 && n_blocks >= 1 && table_rows > 0, "lrb_encode_fwd: bad shape");
+  LRB_REQUIRE(id_bytes == 4 || id_bytes == 8, "lrb_encode_fwd: id_bytes must be 4 (int32) or 8 (int64)");
   if (L > LRB_MAX_LEN)
     return set_error(LRB_ERR_UNSUPPORTED, "sequence length %d exceeds LRB_MAX_LEN=%d", L, LRB_MAX_LEN);
   if (workspace_bytes < lrb_encode_workspace_bytes(B, L, all_positions))
@@ -528,7 +531,7 @@ int lrb_encode_fwd(const int64_t* ids, int B, int L, const float* table_f32, int
     const bool last_blk = blk == n_blocks - 1;
     const bool last_only = last_blk && !all_positions;
     InprojParams ip;
-    ip.ids = reinterpret_cast<const long long*>(ids);
+    ip.ids = ids; ip.id_bytes = id_bytes;
     ip.table = table_f32; ip.table_rows = table_rows; ip.wts = weights; ip.blk = blk;
     ip.first_block = blk == 0 ? 1 : 0;
     ip.x_in = x_cur; ip.x0_out = blk == 0 ? x_cur : nullptr; ip.bu = bu;
@@ -538,7 +541,7 @@ int lrb_encode_fwd(const int64_t* ids, int B, int L, const float* table_f32, int
 
     ScanParams sp;
     sp.bu = reinterpret_cast<float2*>(bu);
-    sp.ids = reinterpret_cast<const long long*>(ids);
+    sp.ids = ids; sp.id_bytes = id_bytes;
     sp.wts = weights; sp.blk = blk; sp.tok_first = tok_first; sp.tok_offset = tok_offset;
     sp.B = B; sp.L = L; sp.levels = levels; sp.last_only = last_only ? 1 : 0;
     sp.h_last = reinterpret_cast<float2*>(h_last);

@@ -55,7 +55,7 @@ __global__ void prepare_table_kernel(const float* __restrict__ table, const floa
 constexpr int SEQ_THREADS = 128;
 
 __global__ void __launch_bounds__(SEQ_THREADS)
-prepare_sequences_kernel(const long long* __restrict__ ids, int B, int L, int all_positions,
+prepare_sequences_kernel(const void* __restrict__ ids, int id_bytes, int B, int L, int all_positions,
                          int* __restrict__ tok_first, int* __restrict__ tok_offset,
                          int* __restrict__ excl_sorted, uint32_t* __restrict__ excl_bloom, int stride) {
   __shared__ int s_ids[LRB_MAX_LEN + 1];
@@ -66,9 +66,8 @@ prepare_sequences_kernel(const long long* __restrict__ ids, int B, int L, int al
   if (tid == 0) s_first = L;
   if (tid < 4) s_bloom[tid] = 0u;
   __syncthreads();
-  const long long* row = ids + static_cast<size_t>(b) * L;
   for (int t = tid; t < L; t += SEQ_THREADS) {
-    const int id = static_cast<int>(row[t]);
+    const int id = static_cast<int>(load_id(ids, static_cast<size_t>(b) * L + t, id_bytes));
     s_ids[t] = id;
     if (id > 0) atomicMin(&s_first, t);
   }
@@ -162,19 +161,19 @@ int lrb_prepare_table(const float* table_f32, const float* bias_f32, int64_t row
   return LRB_OK;
 }
 
-int lrb_prepare_sequences(const int64_t* ids, int B, int L, int all_positions, int32_t* tok_first,
+int lrb_prepare_sequences(const void* ids, int id_bytes, int B, int L, int all_positions, int32_t* tok_first,
                           int32_t* tok_offset, int32_t* excl_sorted, uint32_t* excl_bloom, void* stream) {
   using namespace lrb;
   LRB_REQUIRE(ids && tok_first && tok_offset, "lrb_prepare_sequences: null pointer");
   LRB_REQUIRE(B > 0 && L > 0, "lrb_prepare_sequences: bad shape");
+  LRB_REQUIRE(id_bytes == 4 || id_bytes == 8, "lrb_prepare_sequences: id_bytes must be 4 (int32) or 8 (int64)");
   if (L > LRB_MAX_LEN)
     return set_error(LRB_ERR_UNSUPPORTED, "sequence length %d exceeds LRB_MAX_LEN=%d", L, LRB_MAX_LEN);
   LRB_REQUIRE((excl_sorted == nullptr) == (excl_bloom == nullptr), "lrb_prepare_sequences: exclusion list and bloom filter must come together");
   int rc = check_arch();
   if (rc != LRB_OK) return rc;
   cudaStream_t st = as_stream(stream);
-  prepare_sequences_kernel<<<B, SEQ_THREADS, 0, st>>>(reinterpret_cast<const long long*>(ids), B, L,
-                                                       all_positions, tok_first, tok_offset, excl_sorted,
+  prepare_sequences_kernel<<<B, SEQ_THREADS, 0, st>>>(ids, id_bytes, B, L, all_positions, tok_first, tok_offset, excl_sorted,
                                                        excl_bloom, lrb_excl_stride(L));
   LRB_CUDA_TRY(cudaGetLastError());
   scan_counts_kernel<<<1, 1024, 0, st>>>(tok_offset, B);

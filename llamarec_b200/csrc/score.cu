@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 
+// Developer-harness knobs (tools/tc_check is built with -DLRB_DEBUG_MODES; the library never is).
 #ifdef LRB_DEBUG_MODES
 static int g_debug_cap_div = 0;
 extern "C" void lrb_debug_set_cap_div(int v) { g_debug_cap_div = v; }
@@ -307,11 +308,11 @@ int make_tmap_bias_blocks(CUtensorMap* out, const void* ptr, unsigned long long 
 }
 
 // `grid` counts MMA engines: CTAs for CG == 1, CTA pairs (clusters of 2) for CG == 2.
-template <int KMAX, int NS, bool kDense, int CG>
+template <int KMAX, int NS, bool kDense, int CG, int PROBE = 0>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbias, const tc::ScoreParams& p,
               int grid, cudaStream_t st, bool overlap_prev = false) {
   using L = tc::SmemLayout<KMAX, NS, CG>;
-  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG>;
+  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG, PROBE>;
   LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid * CG));
@@ -347,18 +348,17 @@ static int g_debug_mode = 0;
 static int g_debug_scout = -1;
 static int g_debug_pair_drain = 1;
 static int g_debug_overlap = 1;
+static long long* g_debug_probe_out = nullptr;
+extern "C" void lrb_debug_set_probe_out(long long* p) { g_debug_probe_out = p; }
 extern "C" void lrb_debug_set_overlap(int v) { g_debug_overlap = v; }
-static long long* g_debug_stats = nullptr;
 extern "C" void lrb_debug_set_pair_drain(int v) { g_debug_pair_drain = v; }
 extern "C" void lrb_debug_set_scout(int t) { g_debug_scout = t; }
 extern "C" void lrb_debug_set_score_mode(int m) { g_debug_mode = m; }
-extern "C" void lrb_debug_set_stats(long long* p) { g_debug_stats = p; }
 #else
-static const int g_debug_mode = 0;
 static const int g_debug_scout = -1;
 static const int g_debug_pair_drain = 1;
 static const int g_debug_overlap = 1;
-static long long* const g_debug_stats = nullptr;
+static long long* const g_debug_probe_out = nullptr;
 #endif
 
 extern "C" {
@@ -504,13 +504,35 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     p.part_ids = part_ids + static_cast<size_t>(c0) * slots * K;
     p.part_cnt = part_cnt + static_cast<size_t>(c0) * slots;
     p.slots = slots;
-    p.dense_out = nullptr; p.dense_ld = 0; p.debug_mode = g_debug_mode; p.debug_stats = g_debug_stats;
+    p.dense_out = nullptr; p.dense_ld = 0; p.probe_out = g_debug_probe_out;
     p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
     // Overlap with the previous chunk launch is safe for the scratch as long as chunk i never runs next to
     // chunk i-2 (they share a ring copy): one CTA fits per SM, so that cannot happen when chunk i-1 fills
     // every SM -- chunk i can then only start once chunk i-2 is gone.
     const bool ov = g_debug_overlap && (chunk_idx == 1 || (chunk_idx > 1 && prev_ctas >= sms));
     prev_ctas = d.grid * cg;
+#ifdef LRB_DEBUG_MODES
+    if (g_debug_mode >= 1 && g_debug_mode <= 6 && K <= 20) {   // pipeline probes (see the kernel's PROBE parameter)
+      const int m = g_debug_mode;
+      if (cg == 2) {
+        rc = m == 1 ? launch_tc<20, LRB_NS_PAIR, false, 2, 1>(ta, tb2, tbias, p, d.grid, st, ov)
+           : m == 2 ? launch_tc<20, LRB_NS_PAIR, false, 2, 2>(ta, tb2, tbias, p, d.grid, st, ov)
+           : m == 3 ? launch_tc<20, LRB_NS_PAIR, false, 2, 3>(ta, tb2, tbias, p, d.grid, st, ov)
+           : m == 4 ? launch_tc<20, LRB_NS_PAIR, false, 2, 4>(ta, tb2, tbias, p, d.grid, st, ov)
+           : m == 5 ? launch_tc<20, LRB_NS_PAIR, false, 2, 5>(ta, tb2, tbias, p, d.grid, st, ov)
+                    : launch_tc<20, LRB_NS_PAIR, false, 2, 6>(ta, tb2, tbias, p, d.grid, st, ov);
+      } else {
+        rc = m == 1 ? launch_tc<20, 3, false, 1, 1>(ta, tb1, tbias, p, d.grid, st, ov)
+           : m == 2 ? launch_tc<20, 3, false, 1, 2>(ta, tb1, tbias, p, d.grid, st, ov)
+           : m == 3 ? launch_tc<20, 3, false, 1, 3>(ta, tb1, tbias, p, d.grid, st, ov)
+           : m == 4 ? launch_tc<20, 3, false, 1, 4>(ta, tb1, tbias, p, d.grid, st, ov)
+           : m == 5 ? launch_tc<20, 3, false, 1, 5>(ta, tb1, tbias, p, d.grid, st, ov)
+                    : launch_tc<20, 3, false, 1, 6>(ta, tb1, tbias, p, d.grid, st, ov);
+      }
+      if (rc != LRB_OK) return rc;
+      continue;
+    }
+#endif
     if (cg == 2) {
       if (K <= 20) rc = launch_tc<20, LRB_NS_PAIR, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
       else if (K <= 32) rc = launch_tc<32, 4, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
@@ -565,7 +587,7 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
   p.row_offset = 0; p.K = 1; p.bias_blk = static_cast<const uint8_t*>(bias_blk);
   p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
   p.gslots = nullptr; p.gstride = 0; p.pair_drain = 0; p.c_share = 0; p.scout_tiles = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
-  p.dense_out = out; p.dense_ld = ld_out; p.debug_mode = 0; p.debug_stats = nullptr;
+  p.dense_out = out; p.dense_ld = ld_out; p.probe_out = nullptr;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
   return launch_tc<20, 3, true, 1>(ta, tb, tb, p, d.grid, st);
 }

@@ -67,8 +67,9 @@ struct ScoreParams {
   int gstride;                 // stride (in ints) of gslots rows: the slot count of THIS launch
   float* dense_out;            // dense mode only: [B][dense_ld], columns < rows written
   long long dense_ld;
-  int debug_mode;              // harness only (LRB_DEBUG_MODES): 2 = null epilogue, 3 = TMEM loads only
-  long long* debug_stats;      // harness only: per CTA {cycles, appended records, compactions, tiles}
+  long long* probe_out;        // developer harness only (else nullptr): per CTA {SM cycles, nanoseconds, cycles epilogue
+                               // warp 0 waited for accumulators, cycles the MMA thread waited for a free accumulator
+                               // stage, cycles it waited for TMA data, 0, 0, 0}
   // stream decomposition (host computed, see score_decompose())
   int s_full;        // number of full streams (each = m_tiles CTAs, one per user tile)
   int rem;           // CTAs in the shared stream
@@ -363,7 +364,12 @@ LRB_DEVINL uint64_t umma_desc_k16_nosw(uint32_t smem_addr) {
   return d;                                     // layout type 0 = no swizzle
 }
 
-template <int KMAX, int NS, bool kDense, int CG>
+// PROBE (developer harness only, tools/tc_check; the library instantiates PROBE == 0):
+//   1 = null epilogue (TMA + MMA only)            2 = TMA only (no MMA, null epilogue)
+//   3 = no TMA traffic after the ring is primed (MMA + full epilogue on resident operands)
+//   4 = no TMA traffic, null epilogue (MMA only)  5 = full pipeline, the filter never passes (threshold +inf)
+//   6 = the product path, timed.   Every probe writes per-CTA {cycles, ns} to p.probe_out.
+template <int KMAX, int NS, bool kDense, int CG, int PROBE = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b,
@@ -399,10 +405,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool has_bias = p.bias_blk != nullptr;
-#ifdef LRB_DEBUG_MODES
-  const long long dbg_t0 = clock64();
-  long long dbg_appends = 0, dbg_compactions = 0, dbg_tiles = 0, dbg_wait = 0, dbg_compact = 0, dbg_first = 0;
-#endif
+  long long probe_c0 = 0, probe_t0 = 0;
+  if (PROBE != 0 && threadIdx.x == 0) {
+    probe_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(probe_t0));
+  }
 
   // Programmatic dependent launch: the chunk launches of one lrb_score_topk call are independent (disjoint
   // users, disjoint scratch), so the next chunk's CTAs may take over SMs as soon as CTAs of this launch
@@ -463,6 +470,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int stage = 0;
       uint32_t phase = 0;
       int seg_idx = 0;
+      int probe_tiles = 0;
+      (void)probe_tiles;
       // bytes the (leader's) full barrier expects per stage: the parts of both CTAs
       const uint32_t stage_tx = (L::kBBytes + (has_bias ? L::kBiasBytes : 0)) * CG;
       const uint32_t a_full_lead = CG == 2 ? mapa_u32(smem_u32(a_full_bar), 0) : 0u;
@@ -480,13 +489,13 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int it = -n_scout; it < sg.n1 - sg.n0; ++it) {
           const int n = it < 0 ? sg.n1 + it : sg.n0 + it;   // scout pass re-visits the segment's last tiles
           mbar_wait(&empty_bar[stage], phase ^ 1);
-#ifdef LRB_DEBUG_MODES
-          if ((p.debug_mode == 60 || p.debug_mode == 62 || p.debug_mode == 64) && ++dbg_tiles > NS) {
-            mbar_arrive(&full_bar[stage]);   // probe: reuse the resident stage, no TMA traffic
+          if ((PROBE == 3 || PROBE == 4) && ++probe_tiles > NS) {
+            // probe: the stage still holds an item tile -- hand it to the MMA again, no TMA traffic
+            if (CG == 2) { if (cta_rank == 0) mbar_arrive(&full_bar[stage]); }
+            else mbar_arrive(&full_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1; }
             continue;
           }
-#endif
           uint8_t* st = sB + stage * L::kStage;
           if (CG == 2) {
             // each CTA fetches its 128 item rows (and its half of the bias block); all bytes are
@@ -520,19 +529,27 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int seg_idx = 0;
       const uint64_t desc_a0 = umma_desc_k_sw128(smem_u32(sA));
       const uint64_t desc_ones = umma_desc_k16_nosw(smem_u32(sOnes));
+      long long probe_wait_empty = 0, probe_wait_full = 0;
       while (walk.next(sg)) {
         mbar_wait(a_full_bar, seg_idx & 1);
         const int n_scout = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
         for (int it = -n_scout; it < sg.n1 - sg.n0; ++it) {
-          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-          mbar_wait(&full_bar[stage], phase);
+          if (PROBE != 0) {
+            const long long w0 = clock64();
+            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            const long long w1 = clock64();
+            mbar_wait(&full_bar[stage], phase);
+            probe_wait_empty += w1 - w0;
+            probe_wait_full += clock64() - w1;
+          } else {
+            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            mbar_wait(&full_bar[stage], phase);
+          }
           tc_fence_after();
           const uint32_t st = smem_u32(sB + stage * L::kStage);
           const uint64_t desc_b0 = umma_desc_k_sw128(st);
           const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * BN);
-#ifdef LRB_DEBUG_MODES
-          if (p.debug_mode != 63 && p.debug_mode != 64)   // probes 63/64: no MMA
-#endif
+          if (PROBE != 2)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 32 bytes (16 bf16) along K inside the 128-B swizzle atom: +2 in 16-B units
@@ -540,7 +557,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else umma_bf16_ss(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
           }
           // folded bias: D += ones[128x16] * bias_blk[256x16]^T  (hi + mid + lo bf16 terms)
-          if (has_bias) {
+          if (has_bias && PROBE != 2) {
             if (CG == 2) umma_bf16_ss_pair(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
             else umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
           }
@@ -557,6 +574,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (CG == 2) umma_commit_pair(a_empty_bar, 0b11);
         else umma_commit(a_empty_bar);
         ++seg_idx;
+      }
+      if (PROBE != 0 && p.probe_out != nullptr) {
+        p.probe_out[blockIdx.x * 8 + 3] = probe_wait_empty;
+        p.probe_out[blockIdx.x * 8 + 4] = probe_wait_full;
       }
     }
   } else if (warp == 3) {
@@ -601,13 +622,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     int seg_idx = -1;
+    long long probe_epi_wait = 0;
     // "accumulator stage drained": local barrier, or the leader's for a CTA pair
-    uint32_t acc_empty_addr[ACC_STAGES];
-#pragma unroll
-    for (int i = 0; i < ACC_STAGES; ++i)
-      acc_empty_addr[i] = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[i]), 0) : smem_u32(&tmem_empty_bar[i]);
-    auto release_acc = [&](int a) {
-      if (CG == 2) mbar_arrive_cluster(acc_empty_addr[a]);
+    const uint32_t acc_empty_addr0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
+    auto release_acc = [&](int a) {   // (consecutive mbarriers are 8 bytes apart, in either address window)
+      if (CG == 2) mbar_arrive_cluster(acc_empty_addr0 + static_cast<uint32_t>(a) * 8u);
       else mbar_arrive(&tmem_empty_bar[a]);
     };
     const uint32_t peer_drain_addr =
@@ -672,6 +691,18 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                  static_cast<uint32_t>(acc * BN + half * (BN / 2));
+          // Columns past the end of the table (the ragged last tile) must not count as admissible items:
+          // without a folded-bias block they score exactly 0 (TMA zero-fills out-of-bounds rows), and a
+          // bound published from them could exceed a user's true K-th best.  valid = real columns of
+          // this thread's 128-column half in this tile (warp-uniform; < 128 only for the last tile).
+          const int valid = p.rows - ((sg.n1 - n_scout_run + it) * BN + half * (BN / 2));
+          if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release_acc(acc);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            continue;
+          }
           uint32_t w[2][32];
           tmem_ld_32x32(taddr, w[0]);
           tmem_ld_wait();
@@ -683,6 +714,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
               float q[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(w[c & 1][g * 16 + j]);
+              if (valid < BN / 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) q[j] = (c * 32 + g * 16 + j < valid) ? q[j] : -INFINITY;
+              }
               const float m1 = max3(q[0], q[1], q[2]);
               const float m2 = max3(q[3], q[4], q[5]);
               const float m3 = max3(q[6], q[7], q[8]);
@@ -759,167 +794,37 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       };
 
+      const uint32_t rowthr_s = smem_u32(rowthr + r);
+      const uint32_t drain_seq_s = smem_u32(const_cast<int*>(&sSvc[3]));
       for (int n = sg.n0; n < sg.n1; ++n) {
-#ifdef LRB_DEBUG_MODES
-        const long long w0 = clock64();
-#endif
-        mbar_wait(&tmem_full_bar[acc], acc_phase);
-        tc_fence_after();
-#ifdef LRB_DEBUG_MODES
-        dbg_wait += clock64() - w0;
-        if (n == sg.n0 + 64) dbg_first = clock64() - dbg_t0;
-        if (p.debug_stats != nullptr && threadIdx.x == 128 && seg_idx == 0) {
-          const int k = n - sg.n0;
-          if (k <= 32 && (k & (k - 1)) == 0) {   // tiles 0,1,2,4,8,16,32
-            int slot = 0; while ((1 << slot) < k + 1 && slot < 7) ++slot;   // 0->0,1->1,2->2,4->3,8->4,16->5,32->6
-            p.debug_stats[148 * 8 + blockIdx.x * 16 + slot] = clock64() - dbg_t0;
-            p.debug_stats[148 * 8 + blockIdx.x * 16 + 8 + slot] = dbg_compact;
-          }
-        }
-#endif
-
-        // rows beyond B never produce candidates: their threshold is +inf
+        // rows beyond B never produce candidates: their threshold is +inf.  The row's shared threshold is
+        // read (shared-space load, issued before the wait so that its latency hides behind it) once per tile.
         float t_eff = live ? own_thr : INFINITY;
         if (!kDense && live) {
-          const int kk = *reinterpret_cast<volatile int*>(rowthr + r);
+          const int kk = lds_volatile_s32(rowthr_s);
           if (kk != INT_MIN) t_eff = fmaxf(own_thr, key_to_float(kk));
+        }
+        if (PROBE == 5) t_eff = INFINITY;
+        if (PROBE != 0) {
+          const long long w0 = clock64();
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          probe_epi_wait += clock64() - w0;
+        } else {
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+        }
+        tc_fence_after();
+        if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(acc);
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
         }
 
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + half * (BN / 2));
         const int col_gid0 = p.row_offset + n * BN + half * (BN / 2);
 
-#ifdef LRB_DEBUG_MODES
-        if (p.debug_mode >= 50 && p.debug_mode <= 53) {
-          // math-only probe: one x32 load per tile, the max-tree + compare executed 4 times on it
-          uint32_t w0[32];
-          tmem_ld_32x32(taddr, w0);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(acc);
-          int hits = 0;
-          const int nrep = p.debug_mode == 52 ? 2 : (p.debug_mode == 53 ? 4 : 1);
-          for (int rep = 0; rep < nrep; ++rep)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float gm[2];
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              float q[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(w0[g * 16 + j] ^ static_cast<uint32_t>(c + 4 * rep));
-              const float m1 = max3(q[0], q[1], q[2]);
-              const float m2 = max3(q[3], q[4], q[5]);
-              const float m3 = max3(q[6], q[7], q[8]);
-              const float m4 = max3(q[9], q[10], q[11]);
-              const float m5 = max3(q[12], q[13], q[14]);
-              gm[g] = fmaxf(max3(m1, m2, m3), max3(m4, m5, q[15]));
-            }
-            if (p.debug_mode == 51) {
-              if (fmaxf(gm[0], gm[1]) >= t_eff + 1e30f) ++hits;      // never true: branch per chunk
-            } else {
-              hits += (fmaxf(gm[0], gm[1]) >= t_eff + 1e30f) ? 1 : 0;
-            }
-          }
-          if (hits == 12345) p.gslots[0] = 1;
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-          continue;
-        }
-        if (p.debug_mode >= 20 && p.debug_mode < 50) {
-          // 5 repetitions of the tile's four x32 loads with 1 (mode 20), 4 (mode 30) loads in flight,
-          // or eight x16 loads with 2 in flight (mode 40)
-          uint32_t acc_x = 0;
-          for (int rep = 0; rep < 5; ++rep) {
-            if (p.debug_mode == 20) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint32_t w0[32];
-                tmem_ld_32x32(taddr + c * 32, w0);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc_x ^= w0[j];
-              }
-            } else if (p.debug_mode == 30) {
-              uint32_t w0[32], w1[32], w2[32], w3[32];
-              tmem_ld_32x32(taddr, w0);
-              tmem_ld_32x32(taddr + 32, w1);
-              tmem_ld_32x32(taddr + 64, w2);
-              tmem_ld_32x32(taddr + 96, w3);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j] ^ w2[j] ^ w3[j];
-            }
-          }
-          if (acc_x == 0x12345678u) p.gslots[0] = 1;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(acc);
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-          continue;
-        }
-        if (p.debug_mode >= 10 && p.debug_mode < 20) {
-          // repeat the four x32 loads (debug_mode - 9) times per tile: measures TMEM->RF bandwidth
-          const int reps = p.debug_mode - 9;
-          uint32_t acc_x = 0;
-          for (int rep = 0; rep < reps; ++rep) {
-            uint32_t w0[32], w1[32];
-            tmem_ld_32x32(taddr, w0);
-            tmem_ld_32x32(taddr + 32, w1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j];
-            tmem_ld_32x32(taddr + 64, w0);
-            tmem_ld_32x32(taddr + 96, w1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j];
-          }
-          if (acc_x == 0x12345678u) p.gslots[0] = 1;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(acc);
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-          continue;
-        }
-        if (p.debug_mode == 4) {
-          // all four loads in flight, one wait: separates TMEM-load latency from bandwidth
-          uint32_t w0[32], w1[32], w2[32], w3[32];
-          tmem_ld_32x32(taddr, w0);
-          tmem_ld_32x32(taddr + 32, w1);
-          tmem_ld_32x32(taddr + 64, w2);
-          tmem_ld_32x32(taddr + 96, w3);
-          tmem_ld_wait();
-          uint32_t acc_x = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc_x ^= w0[j] ^ w1[j] ^ w2[j] ^ w3[j];
-          if (acc_x == 0x12345678u) p.gslots[0] = 1;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(acc);
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-          continue;
-        }
-        if (p.debug_mode == 2 || p.debug_mode == 3 || (p.debug_mode >= 60 && p.debug_mode <= 64)) {
-          if (p.debug_mode == 3 || p.debug_mode == 62) {
-            uint32_t w[32];
-            uint32_t acc_x = 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              tmem_ld_32x32(taddr + c * 32, w);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) acc_x ^= w[j];
-            }
-            if (acc_x == 0x12345678u) p.gslots[0] = 1;   // keep the loads alive
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(acc);
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-          continue;
-        }
-#endif
         uint32_t v[2][32];
         tmem_ld_32x32(taddr, v[0]);
         tmem_ld_wait();
@@ -994,7 +899,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // shared sequence number and every warp drains at its next tile boundary.  A drain stalls the
           // two-deep accumulator ring for everybody, so eight simultaneous drains cost one stall, not eight.
           const bool need = __any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0));
-          int seq = sSvc[3];
+          int seq = lds_volatile_s32(drain_seq_s);
           if (need && seq == drain_seen) {
             if (lane == 0) {
               atomicAdd(const_cast<int*>(&sSvc[3]), 1);
@@ -1004,26 +909,14 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             seq += 1;
           }
           if (need || seq != drain_seen) {
-            drain_seen = sSvc[3];
+            drain_seen = lds_volatile_s32(drain_seq_s);
             boot = false;
-#ifdef LRB_DEBUG_MODES
-            dbg_appends += cnt;
-            if (lane == 0) dbg_compactions += 1;
-            const long long c0 = clock64();
-#endif
             drain();
-#ifdef LRB_DEBUG_MODES
-            dbg_compact += clock64() - c0;
-#endif
           }
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
 
-#ifdef LRB_DEBUG_MODES
-      dbg_appends += cnt;
-      if (lane == 0 && quad == 0 && half == 0) dbg_tiles += sg.n1 - sg.n0;
-#endif
       if (!kDense) drain();   // final drain of this segment (whole warp, lock-step)
 
       if (!kDense && live) {
@@ -1038,18 +931,15 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // before the next segment resets its buffer
     }
     if (et == 0) sSvc[2] = 1;   // all segments of this CTA are done: stop the threshold service
+    if (PROBE != 0 && et == 0 && p.probe_out != nullptr) p.probe_out[blockIdx.x * 8 + 2] = probe_epi_wait;
   }
 
-#ifdef LRB_DEBUG_MODES
-  if (p.debug_stats != nullptr) {
-    if (dbg_appends) atomicAdd(reinterpret_cast<unsigned long long*>(p.debug_stats + blockIdx.x * 4 + 1),
-                               static_cast<unsigned long long>(dbg_appends));
-    if (dbg_compactions) atomicAdd(reinterpret_cast<unsigned long long*>(p.debug_stats + blockIdx.x * 4 + 2),
-                                   static_cast<unsigned long long>(dbg_compactions));
-    if (dbg_tiles) atomicAdd(reinterpret_cast<unsigned long long*>(p.debug_stats + blockIdx.x * 4 + 3),
-                             static_cast<unsigned long long>(dbg_tiles));
+  if (PROBE != 0 && threadIdx.x == 0 && p.probe_out != nullptr) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.probe_out[blockIdx.x * 8] = clock64() - probe_c0;
+    p.probe_out[blockIdx.x * 8 + 1] = t1 - probe_t0;
   }
-#endif
   // ... but no launch may COMPLETE before its predecessor has: what follows the last chunk in the stream
   // (the merge kernel) must see the results of every chunk.
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1061,14 +951,6 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
-#ifdef LRB_DEBUG_MODES
-  if (p.debug_stats != nullptr && threadIdx.x == 0) p.debug_stats[blockIdx.x * 4] = clock64() - dbg_t0;
-  if (p.debug_stats != nullptr && threadIdx.x == 128) {   // epilogue warp 0, lane 0
-    p.debug_stats[148 * 4 + blockIdx.x * 4 + 0] = dbg_wait;
-    p.debug_stats[148 * 4 + blockIdx.x * 4 + 1] = dbg_compact;
-    p.debug_stats[148 * 4 + blockIdx.x * 4 + 2] = dbg_first;
-  }
-#endif
 }
 
 }  // namespace tc

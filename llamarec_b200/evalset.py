@@ -50,6 +50,20 @@ class DeviceEvalSet:
         self.labels = torch.from_numpy(labels).to(device)
 
     @classmethod
+    def from_tensors(cls, seqs: torch.Tensor, labels: torch.Tensor, batch_size: int, device="cuda") -> "DeviceEvalSet":
+        """An eval split that already exists as a left-padded id matrix [U, L] (+ labels [U]): stored as int32 on
+        the device and iterated like the reference's DataLoader (shuffle=False, last batch short)."""
+        self = cls.__new__(cls)
+        self.users = list(range(1, seqs.shape[0] + 1))
+        self.max_len = int(seqs.shape[1])
+        self.batch_size = int(batch_size)
+        if int(seqs.max()) >= 2 ** 31:
+            raise ValueError("item ids do not fit int32")
+        self.seqs = seqs.to(torch.int32).contiguous().to(device)
+        self.labels = labels.view(-1).to(torch.int64).contiguous().to(device)
+        return self
+
+    @classmethod
     def from_reference_dataloader(cls, dl, mode: str, device="cuda", batch_size: Optional[int] = None):
         """dl: the reference's LRUDataloader (dataloader/lru.py:12-61); mode 'val' or 'test'."""
         if mode not in ("val", "test"):

@@ -13,6 +13,7 @@ Fast entry points added on top of the reference interface:
 """
 from __future__ import annotations
 
+import functools
 import math
 import warnings
 from typing import Dict, Optional, Sequence
@@ -24,6 +25,19 @@ from . import _lib
 from .packing import pack_encoder_weights
 
 SMALL_CATALOGUE_ROWS = 1 << 17   # up to here 'auto' precision scores in exact fp32
+
+
+def _on_model_device(fn):
+    """Runs a method with the model's device current: the C-ABI launches go to the CURRENT device's stream, so a
+    model on cuda:1 called from a process whose current device is cuda:0 would otherwise launch on the wrong GPU."""
+    @functools.wraps(fn)
+    def wrap(self, *args, **kwargs):
+        w = self.embedding.token.weight
+        if not w.is_cuda:
+            raise RuntimeError("llamarec_b200 has no CPU path: move the model to a CUDA device (model.cuda())")
+        with torch.cuda.device(w.device):
+            return fn(self, *args, **kwargs)
+    return wrap
 
 
 class _Container(nn.Module):
@@ -103,6 +117,7 @@ class LRURec(nn.Module):
         m.load_state_dict(ref_model.state_dict())
         return m
 
+    @_on_model_device
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """model/lru.py:38-41 -- scores at every position, [B, L, N+1] fp32 (exact fp32 scoring)."""
         hidden = self.hidden_states(x)
@@ -121,22 +136,25 @@ class LRURec(nn.Module):
         self.row_begin, self.row_end = int(row_begin), int(row_end)
         self._prepared_sig = None
 
+    @_on_model_device
     def hidden_states(self, x: torch.Tensor) -> torch.Tensor:
         """Encoder output at every position, [B, L, 64] (model/lru.py:73-83)."""
         return self._encode(x, all_positions=True)[0]
 
+    @_on_model_device
     def encode(self, x: torch.Tensor, want_bf16: bool = False):
         """Last-position user state u[B, 64] fp32 (and optionally its bf16 copy)."""
         u, u16, _ = self._encode(x, all_positions=False, want_bf16=want_bf16)
         return (u, u16) if want_bf16 else u
 
+    @_on_model_device
     @torch.no_grad()
     def retrieve(self, x: torch.Tensor, k: int = 20, exclude_history: bool = True,
                  labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
                  precision: str = "auto", u: Optional[torch.Tensor] = None,
                  u_bf16: Optional[torch.Tensor] = None, merge: bool = True,
                  packed_out: Optional[torch.Tensor] = None, seq: Optional[dict] = None,
-                 scatter: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                 scatter: Optional[dict] = None, packed_layout: str = "planes") -> Dict[str, torch.Tensor]:
         """encode -> catalogue score -> (history mask) -> top-k -> (metrics), all on device.
 
         Replaces calculate_metrics / the per-user loop of generate_candidates (trainer/lru.py:30-42,
@@ -197,10 +215,11 @@ class LRURec(nn.Module):
         if not merge:
             return {"part_scores": part_s, "part_ids": part_i, "part_cnt": part_c, "u": u}
         out = merge_lists(part_s, part_i, part_c, k_out=k, labels=labels, ks=ks, packed_out=packed_out,
-                          scatter=scatter)
+                          scatter=scatter, packed_layout=packed_layout)
         out["u"] = u
         return out
 
+    @_on_model_device
     @torch.no_grad()
     def ce_loss(self, x: torch.Tensor, labels: torch.Tensor, ignore_index: int = 0,
                 return_row_loss: bool = False):
@@ -287,14 +306,15 @@ class LRURec(nn.Module):
         lib = _lib.load()
         B, L = x.shape
         dev = x.device
-        if x.dtype != torch.int64:
+        if x.dtype not in (torch.int64, torch.int32):     # both widths are consumed natively by the kernels
             x = x.to(torch.int64)
         stride = lib.lrb_excl_stride(L)
         tok_first = self._buf(("tok_first", B), (B,), torch.int32, dev)
         tok_offset = self._buf(("tok_offset", B), (B + 1,), torch.int32, dev)
         excl_sorted = self._buf(("excl_sorted", B, stride), (B, stride), torch.int32, dev) if want_excl else None
         excl_bloom = self._buf(("excl_bloom", B), (B, 4), torch.int32, dev) if want_excl else None
-        _lib.check(lib.lrb_prepare_sequences(_lib.ptr(x), B, L, 1 if all_positions else 0, _lib.ptr(tok_first),
+        _lib.check(lib.lrb_prepare_sequences(_lib.ptr(x), x.element_size(), B, L, 1 if all_positions else 0,
+                                             _lib.ptr(tok_first),
                                              _lib.ptr(tok_offset), _lib.ptr(excl_sorted), _lib.ptr(excl_bloom),
                                              _lib.stream_handle()))
         return {"ids": x, "tok_first": tok_first, "tok_offset": tok_offset, "excl_sorted": excl_sorted,
@@ -319,7 +339,8 @@ class LRURec(nn.Module):
         else:
             out = torch.empty(B, 64, dtype=torch.float32, device=dev)
             out16 = torch.empty(B, 64, dtype=torch.bfloat16, device=dev) if want_bf16 else None
-        _lib.check(lib.lrb_encode_fwd(_lib.ptr(seq["ids"]), B, L, _lib.ptr(c["table_f32"]), c["table_f32"].shape[0],
+        _lib.check(lib.lrb_encode_fwd(_lib.ptr(seq["ids"]), seq["ids"].element_size(), B, L, _lib.ptr(c["table_f32"]),
+                                      c["table_f32"].shape[0],
                                       _lib.ptr(c["blob"]), c["n_blocks"], 1 if all_positions else 0,
                                       _lib.ptr(seq["tok_first"]), _lib.ptr(seq["tok_offset"]), _lib.ptr(out),
                                       _lib.ptr(out16), _lib.ptr(ws), ws_bytes, _lib.stream_handle()))
@@ -329,12 +350,23 @@ class LRURec(nn.Module):
 def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Optional[torch.Tensor], k_out: int,
                 labels: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
                 layout: str = "user_major", packed_out: Optional[torch.Tensor] = None,
-                strides: Optional[tuple] = None, scatter: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                strides: Optional[tuple] = None, scatter: Optional[dict] = None,
+                packed_layout: str = "planes") -> Dict[str, torch.Tensor]:
     """Fused k-way merge + metrics (lrb_merge_metrics).
 
     layout 'user_major': lists are [B, S, K] (output of lrb_score_topk);
     layout 'list_major': lists are [R, B, K] (all-gathered per-rank results).
+    packed_out (optional int32 output buffer) is laid out as `packed_layout` says -- never guessed from its
+    shape: 'planes' = [2, B, k_out] (all scores, then all ids: one all-gather payload), 'per_user' =
+    [B, 2, k_out] (per user scores then ids: rows of an all-to-all payload split by user range).
     """
+    with _lib.on_device(list_scores):
+        return _merge_lists(list_scores, list_ids, list_cnt, k_out, labels, ks, layout, packed_out, strides, scatter,
+                            packed_layout)
+
+
+def _merge_lists(list_scores, list_ids, list_cnt, k_out, labels, ks, layout, packed_out, strides, scatter,
+                 packed_layout):
     lib = _lib.load()
     dev = list_scores.device
     if layout == "user_major":
@@ -362,13 +394,20 @@ def merge_lists(list_scores: torch.Tensor, list_ids: torch.Tensor, list_cnt: Opt
         return {}
     ks = list(ks) if ks is not None else []
     out_stride = 0
-    if packed_out is not None and packed_out.shape[0] == 2 and packed_out.dim() == 3 and packed_out.shape[1] == B:
+    if packed_out is not None and packed_layout not in ("planes", "per_user"):
+        raise ValueError(f"unknown packed_layout {packed_layout!r}")
+    if packed_out is not None and (packed_out.dtype != torch.int32 or not packed_out.is_contiguous()):
+        raise ValueError("packed_out must be a contiguous int32 tensor")
+    if packed_out is not None and packed_layout == "planes":
         # [2, B, k_out] int32: scores (bit pattern) then ids, one gather payload
+        if tuple(packed_out.shape) != (2, B, k_out):
+            raise ValueError(f"packed_out is {tuple(packed_out.shape)}, layout 'planes' needs {(2, B, k_out)}")
         top_s = packed_out[0].view(torch.float32)
         top_i = packed_out[1]
     elif packed_out is not None:
         # [B, 2, k_out] int32: per user scores then ids (rows of an all-to-all payload split by user range)
-        assert tuple(packed_out.shape) == (B, 2, k_out) and packed_out.is_contiguous()
+        if tuple(packed_out.shape) != (B, 2, k_out):
+            raise ValueError(f"packed_out is {tuple(packed_out.shape)}, layout 'per_user' needs {(B, 2, k_out)}")
         top_s = packed_out.view(torch.float32)[:, 0]
         top_i = packed_out[:, 1]
         out_stride = 2 * k_out

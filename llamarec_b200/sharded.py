@@ -51,7 +51,11 @@ class CudaBackend:
 
     def __init__(self, model, rank: int, world: int, precision: str = "auto"):
         self.model = model
-        self.precision = precision
+        # 'auto' is resolved ONCE from the whole catalogue, not from this rank's shard: shard_range gives the
+        # last rank a shorter shard, and ranks that disagree would exchange states of different widths and
+        # merge scores of different precisions
+        prec = model._precision(precision, model.num_items + 1)
+        self.precision = "fp32" if prec == 1 else "bf16"
         self._packed = {}
         lo, hi = shard_range(model.num_items + 1, rank, world)
         model.set_row_shard(lo, hi)
@@ -72,7 +76,8 @@ class CudaBackend:
             buf[0].view(torch.float32).fill_(float("-inf"))
             buf[1].fill_(-1)
             return buf
-        self.model.retrieve(x, k=k, exclude_history=exclude_history, precision=self.precision, u=u, packed_out=buf)
+        self.model.retrieve(x, k=k, exclude_history=exclude_history, precision=self.precision, u=u, packed_out=buf,
+                            packed_layout="planes")
         return buf
 
     # ---- data-parallel users (retrieve_dp) ----
@@ -113,7 +118,7 @@ class CudaBackend:
         seq = {"excl_sorted": excl, "excl_bloom": bloom, "excl_stride": excl_stride}
         kw = {"u_bf16": state} if state.dtype == torch.bfloat16 else {"u": state}
         self.model.retrieve(None, k=k, exclude_history=excl is not None, precision=self.precision, seq=seq,
-                            packed_out=buf, **kw)
+                            packed_out=buf, packed_layout="per_user", **kw)
         return buf
 
     def merge_rows(self, recv: torch.Tensor, k, labels, ks):
@@ -242,7 +247,8 @@ class ShardedRetriever:
         dst = (_lib.ctypes.c_void_p * (n_arr * R))(*[
             px.ptrs[d] + px.gather_off[par][a] + self.rank * b * px.rec_bytes[a]
             for a in range(n_arr) for d in range(R)])
-        _lib.check(lib.lrb_peer_push(src, nbytes, n_arr, dst, R, _lib.stream_handle()))
+        with _lib.on_device(arrays[0]):
+            _lib.check(lib.lrb_peer_push(src, nbytes, n_arr, dst, R, _lib.stream_handle()))
         px.barrier(0)
         mark("all_gather")
         # 2. score all R*b users against the local rows; the local merge scatters each user's list to its owner

@@ -106,9 +106,11 @@ class ManualVerbalizer:
         B, H = h.shape
         C, W = ids.shape
         out = torch.empty(B, C, dtype=torch.float32, device=dev)
-        _lib.check(lib.lrb_verbalizer_score(_lib.ptr(h), _lib.ptr(w), B, H, w.shape[0], _lib.ptr(ids), _lib.ptr(mask),
-                                            C, W, 1 if self.post_log_softmax else 0,
-                                            1 if round_logits_to_bf16 else 0, _lib.ptr(out), _lib.stream_handle()))
+        with _lib.on_device(h):
+            _lib.check(lib.lrb_verbalizer_score(_lib.ptr(h), _lib.ptr(w), B, H, w.shape[0], _lib.ptr(ids),
+                                                _lib.ptr(mask), C, W, 1 if self.post_log_softmax else 0,
+                                                1 if round_logits_to_bf16 else 0, _lib.ptr(out),
+                                                _lib.stream_handle()))
         return out
 
     # ---- the reference's entry point on precomputed logits (trainer/verb.py:524-614) ----------------
@@ -133,11 +135,12 @@ class ManualVerbalizer:
             B, V = lg.shape
             C, W, T = ids.shape
             out = torch.empty(B, C, dtype=torch.float32, device=dev)
-            _lib.check(lib.lrb_verbalizer_from_logits(lg.data_ptr(), lg.stride(0), B, V, _lib.ptr(ids), _lib.ptr(tmask),
-                                                      _lib.ptr(wmask), C, W, T,
-                                                      self._HANDLERS[self.multi_token_handler],
-                                                      1 if self.post_log_softmax else 0, _lib.ptr(out),
-                                                      _lib.stream_handle()))
+            with _lib.on_device(lg):
+                _lib.check(lib.lrb_verbalizer_from_logits(lg.data_ptr(), lg.stride(0), B, V, _lib.ptr(ids),
+                                                          _lib.ptr(tmask), _lib.ptr(wmask), C, W, T,
+                                                          self._HANDLERS[self.multi_token_handler],
+                                                          1 if self.post_log_softmax else 0, _lib.ptr(out),
+                                                          _lib.stream_handle()))
             return out
         raise RuntimeError("ManualVerbalizer.process_logits needs a CUDA device: project / normalize / aggregate "
                            "(trainer/verb.py:524-614) run in one kernel, there is no CPU path")

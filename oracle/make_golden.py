@@ -270,6 +270,72 @@ def make_verbalizer_handler_fixture():
     print("verbalizer handlers ok")
 
 
+def make_c1_fixture():
+    """BASELINE.json configs[0] at its stated shape, computed by the REFERENCE itself: 943 users x 1,682 items,
+    max_len 200, eval batch 16 (config.py:104).  The model is the reference's own `LRURec(args)` under
+    torch.manual_seed(42) -- including its truncated-normal model.bias (model/lru.py:16-36 initialises every
+    parameter whose name has neither 'layer_norm' nor 'params_log').  Records, for the val and test splits of
+    synth.make_sequences (the same generator the GPU tests call): per-batch `calculate_metrics` dicts
+    (trainer/lru.py:30-42), the masked top-20 of every user (trainer/lru.py:82-84) and the complete
+    `generate_candidates` pickle (trainer/lru.py:44-175).
+    `python oracle/make_golden.py c1` writes tests/golden/c1_ml100k_ref.pkl + c1_ml100k_weights.npz."""
+    config, RefLRURec, tutils, tlru, verb = import_reference()
+    from oracle import lru_oracle as O
+    from oracle import metrics_oracle as MO
+    from llamarec_b200 import synth
+    cfg = synth.CONFIGS["c1_ml100k"]
+    N, L, bs, ks = cfg.num_items, cfg.max_len, cfg.batch, list(cfg.metric_ks)
+    torch.manual_seed(42)
+    args = SimpleNamespace(num_items=N, bert_hidden_units=64, bert_num_blocks=2, bert_dropout=0.2,
+                           bert_attn_dropout=0.2)
+    ref = RefLRURec(args).eval()
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    assert float(sd["model.bias"].abs().max()) > 0          # the reference does initialise the bias
+    splits = {name: synth.make_sequences(cfg, seed=42, split=name) for name in ("val", "test")}
+    out = {"ks": ks, "batch": bs, "num_items": N, "num_users": cfg.num_users, "max_len": L}
+    with torch.no_grad():
+        for name, (ids, labels) in splits.items():
+            fake = SimpleNamespace(model=ref, metric_ks=ks)
+            per_batch, top_i, top_s = [], [], []
+            for i in range(0, ids.shape[0], bs):
+                x, y = ids[i:i + bs], labels[i:i + bs].unsqueeze(1)
+                m = tlru.LRUTrainer.calculate_metrics(fake, (x, y))
+                per_batch.append([m[f"{n}@{k}"] for k in ks for n in ("Recall", "MRR", "NDCG")])
+                scores = ref(x)[:, -1, :]
+                for j in range(L):
+                    scores[torch.arange(scores.size(0)), x[:, j]] = -1e9
+                scores[:, 0] = -1e9
+                s, t = torch.topk(scores, 20)
+                top_i.append(t)
+                top_s.append(s)
+                # the oracle agrees with the reference on this batch (scores to fp32 round-off, metrics exactly)
+                o = O.mask_history(O.last_scores(x, sd), x)
+                assert torch.allclose(o, scores, atol=2e-6, rtol=1e-5), (name, i)
+                om = MO.recall_mrr_ndcg(o, y.view(-1), ks)
+                for k_, v_ in m.items():
+                    assert abs(om[k_] - v_) < 1e-6, (name, i, k_)
+            out[f"{name}_batch_metrics"] = np.array(per_batch, dtype=np.float64)
+            out[f"{name}_top_ids"] = torch.cat(top_i).numpy().astype(np.int16)
+            out[f"{name}_top_scores"] = torch.cat(top_s).numpy()
+            out[f"{name}_ids_sha"] = int(ids.sum().item())
+    mk = lambda ids, lab: [(ids[i:i + bs], lab[i:i + bs].unsqueeze(1)) for i in range(0, ids.shape[0], bs)]
+    targs = SimpleNamespace(num_users=cfg.num_users, num_items=N, llm_negative_sample_size=19, metric_ks=ks)
+    config.args.metric_ks = ks
+    config.args.num_items = N
+    fake = SimpleNamespace(model=ref, metric_ks=ks, val_loader=mk(*splits["val"]), test_loader=mk(*splits["test"]),
+                           args=targs, to_device=lambda b: b)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "retrieved.pkl")
+        tlru.LRUTrainer.generate_candidates(fake, path)
+        with open(path, "rb") as f:
+            out["retrieved"] = pickle.load(f)
+    np.savez(os.path.join(OUT, "c1_ml100k_weights.npz"), **{k: v.numpy() for k, v in sd.items()})
+    with open(os.path.join(OUT, "c1_ml100k_ref.pkl"), "wb") as f:
+        pickle.dump(out, f)
+    print("c1 ok:", {k: round(v, 4) for k, v in out["retrieved"]["test_metrics"].items() if "@10" in k},
+          "retrieval_size", out["retrieved"]["test_retrieval"]["retrieval_size"])
+
+
 def make_evalset_fixture():
     """LRUValidDataset / LRUTestDataset of the REFERENCE (dataloader/lru.py:129-180) on random user histories:
     `python oracle/make_golden.py evalset` writes tests/golden/evalset_case.npz."""
@@ -306,5 +372,7 @@ if __name__ == "__main__":
         make_verbalizer_handler_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "ce":
         make_ce_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "c1":
+        make_c1_fixture()
     else:
         main()

@@ -131,12 +131,25 @@ def test_generate_candidates_matches_reference_pickle(model, tmp_path):
     assert set(ours.keys()) == set(ref.keys())
     for key in ("val_users", "test_users", "non_test_users", "test_labels"):
         assert ours[key] == ref[key], key
+    # candidate lists: identical, or -- the fixture records the reference's scores of every test user --
+    # differing only among items whose reference scores tie within the tolerance (torch.topk's tie order is
+    # implementation-defined)
+    ref_scores = g.get("test_scores")
     for key in ("val_candidates", "test_candidates", "test_probs"):
         assert len(ours[key]) == len(ref[key])
-        same = sum(a == b for a, b in zip(ours[key], ref[key]))
-        assert same >= len(ref[key]) - 1, (key, same, len(ref[key]))     # at most one tie-swapped list
-        for a, b in zip(ours[key], ref[key]):
-            assert sorted(a)[:1] == sorted(a)[:1] and len(a) == len(b)
+        n_diff = 0
+        for idx, (a, b) in enumerate(zip(ours[key], ref[key])):
+            assert len(a) == len(b) and len(set(a)) == len(a), (key, idx)
+            if a == b:
+                continue
+            n_diff += 1
+            assert sorted(a)[:-1] == sorted(b)[:-1] or sorted(a) == sorted(b) or len(set(a) ^ set(b)) <= 2, (key, idx, a, b)
+            if ref_scores is not None and key == "test_probs":
+                sc = ref_scores[idx]
+                for pa, pb in zip(a, b):
+                    if pa != pb:
+                        assert abs(sc[pa] - sc[pb]) <= RTOL * max(1.0, abs(sc[pb])), (key, idx, pa, pb)
+        assert n_diff <= 1, (key, n_diff, len(ref[key]))                 # at most one tie-swapped list
     for key in ("val_metrics", "test_metrics"):
         for k, v in ref[key].items():
             assert abs(ours[key][k] - v) < 5e-5, (key, k)
@@ -374,6 +387,38 @@ def test_peer_push_and_scatter_merge_with_local_destinations(games_model):
     merge_lists(part["part_scores"], part["part_ids"], part["part_cnt"], k_out=20, scatter=scatter)
     got = torch.cat(recv)
     assert torch.equal(got[:, 0].view(torch.float32), plain["scores"]) and torch.equal(got[:, 1], plain["ids"])
+
+
+def test_scout_bound_ignores_pad_columns_of_the_ragged_last_tile():
+    """Adversarial case for the union bound's scout pass (zero bias => no folded-bias block => TMA zero-fills the
+    pad columns of the last item tile, which then score exactly 0.0).  Every real score is negative, the second
+    half of the catalogue scores ten times lower than the first, and rows % 256 = 20 leaves both column halves
+    of the last tile with more all-pad 16-item groups than the c = 5 entries a stream must publish: if pad
+    columns counted as admissible items, the last stream would publish 0.0, the union bound would sit at the
+    first stream's 5th best and ranks 11..20 of every list would be dropped.  9472 users = 37 pair tiles = two
+    full streams, no shared stream (the chunk shape of every multi-GPU step)."""
+    rows = 256 * 274 + 20                                    # 70,164 rows: 137 tiles per stream >= 128 => scout on
+    n, B, K = rows - 1, 9472, 20
+    g = torch.Generator().manual_seed(3)
+    table = torch.rand(rows, 64, generator=g) * 0.01 + 0.01
+    table[rows // 2:] *= 10.0
+    m = LRURec(_args(n))
+    with torch.no_grad():
+        m.embedding.token.weight.copy_(table)
+        m.model.bias.zero_()
+    m = m.cuda().eval()
+    u = -(torch.rand(B, 64, generator=g) + 0.5)
+    ids = torch.zeros(B, 50, dtype=torch.int64)
+    ids[:, -9:] = torch.randint(1, rows, (B, 9), generator=g)
+    ids[::7, -9:] = torch.randint(rows - 16 * 256, rows, (B // 7 + 1, 9), generator=g)[: len(ids[::7])]   # E > 0
+    u16 = u.to(torch.bfloat16)
+    res = m.retrieve(ids.cuda(), k=K, exclude_history=True, precision="bf16", u=u.cuda(), u_bf16=u16.cuda())
+    got_i, got_s = res["ids"].cpu(), res["scores"].cpu()
+    assert (got_i >= 1).all() and (got_s < 0).all()          # 20 real items for every user, nothing dropped
+    sel = torch.arange(0, B, 37)                             # 256 users spread over all 37 pair tiles
+    t16 = table.to(torch.bfloat16).float()
+    ref_s, ref_i = O.retrieve(ids[sel], {}, K, u=u16[sel].float(), table=t16, bias=torch.zeros(rows))
+    assert_topk_equivalent(got_i[sel].numpy(), got_s[sel].numpy(), ref_i.numpy(), ref_s.numpy(), rtol=1e-5)
 
 
 def test_full_size_10m_catalogue_properties():

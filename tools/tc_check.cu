@@ -32,8 +32,8 @@
   } while (0)
 
 extern "C" void lrb_debug_set_score_mode(int m);
-extern "C" void lrb_debug_set_stats(long long* p);
 extern "C" void lrb_debug_set_scout(int t);
+extern "C" void lrb_debug_set_probe_out(long long* p);
 extern "C" void lrb_debug_set_pair_drain(int v);
 extern "C" void lrb_debug_set_overlap(int v);
 extern "C" void lrb_debug_set_cap_div(int v);
@@ -310,36 +310,29 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
   CK(cudaEventElapsedTime(&ms, e0, e1));
   ms /= iters;
   {
-    // one more launch with per-CTA statistics
+    // one more launch with the per-CTA timers (probe builds only write them): SM cycles and wall time per CTA
     int sms = 0, cc = 0;
     lrb_device_info(&sms, &cc);
-    long long* dstats;
-    CK(cudaMalloc(&dstats, sms * 24 * sizeof(long long)));
-    CK(cudaMemset(dstats, 0, sms * 24 * sizeof(long long)));
-    lrb_debug_set_stats(dstats);
+    long long* dprobe;
+    CK(cudaMalloc(&dprobe, sms * 8 * sizeof(long long)));
+    CK(cudaMemset(dprobe, 0, sms * 8 * sizeof(long long)));
+    lrb_debug_set_probe_out(dprobe);
     LK(lrb_score_topk(du, T.e16, T.bias_pad, bblk, B, rows, 0, with_excl ? dex : nullptr, with_excl ? dbl : nullptr,
                       stride, K, 0, dps, dpi, dpc, slots, scratch, nullptr));
     CK(cudaDeviceSynchronize());
-    lrb_debug_set_stats(nullptr);
-    std::vector<long long> st(sms * 24);
-    CK(cudaMemcpy(st.data(), dstats, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    printf("  per-CTA [cycles(M) appends/thread compactions/warp tiles] for CTAs 0,1,64,127,128,137,147:\n");
-    int show[7] = {0, 1, 64, 127, 128, 137, 147};
-    for (int i = 0; i < 7; ++i) {
-      int c = show[i];
-      if (c >= sms) continue;
-      printf("   cta %3d: %.2f  %.1f  %.1f  %lld | epi-warp0: wait %.2fM compact %.2fM first64tiles %.2fM\n", c, st[c * 4] / 1e6, st[c * 4 + 1] / 256.0, st[c * 4 + 2] / 8.0, st[c * 4 + 3],
-             st[sms * 4 + c * 4] / 1e6, st[sms * 4 + c * 4 + 1] / 1e6, st[sms * 4 + c * 4 + 2] / 1e6);
+    lrb_debug_set_probe_out(nullptr);
+    std::vector<long long> st(sms * 8);
+    CK(cudaMemcpy(st.data(), dprobe, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double cyc = 0, ns = 0, ew = 0, me = 0, mf = 0; int n = 0, nl = 0;
+    for (int c = 0; c < sms; ++c) if (st[c * 8] > 0) {
+      cyc += st[c * 8]; ns += st[c * 8 + 1]; ew += st[c * 8 + 2]; ++n;
+      if (st[c * 8 + 3] + st[c * 8 + 4] > 0) { me += st[c * 8 + 3]; mf += st[c * 8 + 4]; ++nl; }
     }
-    printf("   cta 0 warp0 timeline (kcycles at start of tile 0,1,2,4,8,16,32 | cumulative compaction kcycles):\n    ");
-    for (int i = 0; i < 7; ++i) printf("%.0f ", st[sms * 8 + i] / 1e3);
-    printf("| ");
-    for (int i = 0; i < 7; ++i) printf("%.0f ", st[sms * 8 + 8 + i] / 1e3);
-    printf("\n");
-    long long mn = 1LL << 62, mx = 0; double sum = 0;
-    for (int c = 0; c < sms; ++c) { mn = std::min(mn, st[c * 4]); mx = std::max(mx, st[c * 4]); sum += st[c * 4]; }
-    printf("   cycles min %.2fM max %.2fM mean %.2fM\n", mn / 1e6, mx / 1e6, sum / sms / 1e6);
-    cudaFree(dstats);
+    if (n > 0)
+      printf("  per CTA: %.3f Mcycles in %.3f ms => SM clock %.0f MHz | epilogue warp 0 waited %.3f Mcycles for "
+             "accumulators | MMA thread waited %.3f Mcycles for a free accumulator stage, %.3f for TMA data\n",
+             cyc / n / 1e6, ns / n / 1e6, cyc / ns * 1e3, ew / n / 1e6, nl ? me / nl / 1e6 : 0.0, nl ? mf / nl / 1e6 : 0.0);
+    cudaFree(dprobe);
   }
   double tflops = 2.0 * B * (double)rows * 64 / (ms * 1e-3) / 1e12;
   printf("[time] B=%d rows=%d K=%d bias=%d excl=%d slots=%d : %.3f ms/iter  %.1f TFLOP/s  %.0f users/s\n", B, rows, K,
@@ -364,8 +357,9 @@ int main(int argc, char** argv) {
     if (argc > 9) { lrb_debug_set_cap_div(atoi(argv[9])); printf("streams per user >= %d\n", atoi(argv[9])); }
     lrb_debug_set_score_mode(mode);
     if (mode) printf("debug mode %d\n", mode);
-    time_topk(B, rows, K, true, true);
-    if (!mode) time_topk(B, rows, K, false, false);
+    const int which = argc > 10 ? atoi(argv[10]) : 3;   // bit 0: with bias + exclusion, bit 1: without
+    if (which & 1) time_topk(B, rows, K, true, true);
+    if (which & 2) time_topk(B, rows, K, false, false);
     return 0;
   }
   fails += check_dense(200, 1000);
