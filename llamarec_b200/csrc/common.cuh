@@ -225,6 +225,24 @@ LRB_DEVINL void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_
       "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA load multicast to the CTAs of `cta_mask`: the tile lands at the same shared-memory offset in every destination
+// CTA and its bytes are accounted on the mbarrier at the same offset of `bar` in every destination CTA.
+LRB_DEVINL void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
+      "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit of a single-CTA MMA stream that arrives on the barrier at the same offset in every CTA of
+// `cta_mask` (the shared-memory stage it frees is refilled by multicast loads of all of them).
+LRB_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
 LRB_DEVINL void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                    smem_u32(smem_result)),

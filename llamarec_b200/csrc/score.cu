@@ -212,7 +212,7 @@ Decomp decompose(int B, long long rows, int units, int bm = tc::BM) {
     d.full_tiles = d.n_tiles - d.y_tiles;
   }
   d.grid = d.s_full * d.m_tiles + d.rem;
-  d.slots = 2 * (d.s_full + (d.rem > 0 ? 2 : 0));
+  d.slots = tc::SLOT_PARTS * (d.s_full + (d.rem > 0 ? 2 : 0));
   return d;
 }
 
@@ -307,16 +307,20 @@ int make_tmap_bias_blocks(CUtensorMap* out, const void* ptr, unsigned long long 
   return LRB_OK;
 }
 
+// Epilogue warps of the kernel variant that serves list length K: 16 (four 64-column parts per tile) for K <= 20,
+// 8 (two 128-column parts) for the longer lists, whose per-thread candidate sets leave no room for 512 threads.
+inline int epilogue_warps_for(int K) { return K <= 20 ? LRB_EW20 : 8; }
+
 // `grid` counts MMA engines: CTAs for CG == 1, CTA pairs (clusters of 2) for CG == 2.
-template <int KMAX, int NS, bool kDense, int CG, int PROBE = 0>
+template <int KMAX, int NS, bool kDense, int CG, int EW, int PROBE = 0>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbias, const tc::ScoreParams& p,
               int grid, cudaStream_t st, bool overlap_prev = false) {
-  using L = tc::SmemLayout<KMAX, NS, CG>;
-  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG, PROBE>;
+  using L = tc::SmemLayout<KMAX, NS, CG, EW>;
+  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG, EW, PROBE>;
   LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid * CG));
-  cfg.blockDim = dim3(tc::THREADS);
+  cfg.blockDim = dim3(128 + EW * 32);
   cfg.dynamicSmemBytes = L::kAlloc;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -383,7 +387,7 @@ static size_t gslots_bytes(int B) {
   if (sms <= 0) sms = 148;
   size_t m_tiles = (static_cast<size_t>(B) + lrb::tc::BM - 1) / lrb::tc::BM;
   if (m_tiles > static_cast<size_t>(sms)) m_tiles = static_cast<size_t>(sms);   // one launch never covers more
-  const size_t max_slots = 2 * (static_cast<size_t>(sms) / m_tiles + 2);
+  const size_t max_slots = lrb::tc::SLOT_PARTS * (static_cast<size_t>(sms) / m_tiles + 2);
   // (+1 tile: CTA pairs pad the user tiles to an even count)
   return ((m_tiles + 1) * lrb::tc::BM * max_slots * sizeof(int) + 255) & ~static_cast<size_t>(255);
 }
@@ -402,7 +406,7 @@ static size_t gslots_chunk_bytes(int cap) {
 static size_t ring_bytes() {
   int sms = lrb::device_sm_count();
   if (sms <= 0) sms = 148;
-  return static_cast<size_t>(sms) * lrb::tc::EPI_THREADS * lrb::tc::RING_GROUPS * lrb::tc::RING_REC_BYTES;
+  return static_cast<size_t>(sms) * 512 * lrb::tc::RING_GROUPS * lrb::tc::RING_REC_BYTES;   // up to 16 epilogue warps
 }
 
 // layout: [n_chunks x union-bound slots of one chunk][2 x candidate rings (consecutive chunk launches overlap)]
@@ -492,8 +496,9 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     p.pair_drain = g_debug_pair_drain;
     p.ring = static_cast<uint8_t*>(scratch) + n_chunks * gs_chunk + (chunk_idx & 1) * ring_bytes();
     {
-      // entries each of the 2*s_full full-stream threads of a user must hold for the union bound
-      const int c = d.s_full > 0 ? (K + 2 * d.s_full - 1) / (2 * d.s_full) : 99;
+      // entries each of the PARTS*s_full full-stream threads of a user must hold for the union bound
+      const int parts = epilogue_warps_for(K) / 4;
+      const int c = d.s_full > 0 ? (K + parts * d.s_full - 1) / (parts * d.s_full) : 99;
       p.c_share = c <= tc::MAX_C_SHARE ? c : 0;
       // scout pass: worth its T0 extra tiles when the union bound exists and segments are long enough
       const long long seg_tiles = d.s_full > 0 ? d.full_tiles / d.s_full : 0;
@@ -515,32 +520,30 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
     if (g_debug_mode >= 1 && g_debug_mode <= 6 && K <= 20) {   // pipeline probes (see the kernel's PROBE parameter)
       const int m = g_debug_mode;
       if (cg == 2) {
-        rc = m == 1 ? launch_tc<20, LRB_NS_PAIR, false, 2, 1>(ta, tb2, tbias, p, d.grid, st, ov)
-           : m == 2 ? launch_tc<20, LRB_NS_PAIR, false, 2, 2>(ta, tb2, tbias, p, d.grid, st, ov)
-           : m == 3 ? launch_tc<20, LRB_NS_PAIR, false, 2, 3>(ta, tb2, tbias, p, d.grid, st, ov)
-           : m == 4 ? launch_tc<20, LRB_NS_PAIR, false, 2, 4>(ta, tb2, tbias, p, d.grid, st, ov)
-           : m == 5 ? launch_tc<20, LRB_NS_PAIR, false, 2, 5>(ta, tb2, tbias, p, d.grid, st, ov)
-                    : launch_tc<20, LRB_NS_PAIR, false, 2, 6>(ta, tb2, tbias, p, d.grid, st, ov);
+        rc = m == 1 ? launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 1>(ta, tb2, tbias, p, d.grid, st, ov)
+           : m == 2 ? launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 2>(ta, tb2, tbias, p, d.grid, st, ov)
+           : m == 4 ? launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 4>(ta, tb2, tbias, p, d.grid, st, ov)
+           : m == 5 ? launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 5>(ta, tb2, tbias, p, d.grid, st, ov)
+                    : launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 6>(ta, tb2, tbias, p, d.grid, st, ov);
       } else {
-        rc = m == 1 ? launch_tc<20, 3, false, 1, 1>(ta, tb1, tbias, p, d.grid, st, ov)
-           : m == 2 ? launch_tc<20, 3, false, 1, 2>(ta, tb1, tbias, p, d.grid, st, ov)
-           : m == 3 ? launch_tc<20, 3, false, 1, 3>(ta, tb1, tbias, p, d.grid, st, ov)
-           : m == 4 ? launch_tc<20, 3, false, 1, 4>(ta, tb1, tbias, p, d.grid, st, ov)
-           : m == 5 ? launch_tc<20, 3, false, 1, 5>(ta, tb1, tbias, p, d.grid, st, ov)
-                    : launch_tc<20, 3, false, 1, 6>(ta, tb1, tbias, p, d.grid, st, ov);
+        rc = m == 1 ? launch_tc<20, 2, false, 1, LRB_EW20, 1>(ta, tb1, tbias, p, d.grid, st, ov)
+           : m == 2 ? launch_tc<20, 2, false, 1, LRB_EW20, 2>(ta, tb1, tbias, p, d.grid, st, ov)
+           : m == 4 ? launch_tc<20, 2, false, 1, LRB_EW20, 4>(ta, tb1, tbias, p, d.grid, st, ov)
+           : m == 5 ? launch_tc<20, 2, false, 1, LRB_EW20, 5>(ta, tb1, tbias, p, d.grid, st, ov)
+                    : launch_tc<20, 2, false, 1, LRB_EW20, 6>(ta, tb1, tbias, p, d.grid, st, ov);
       }
       if (rc != LRB_OK) return rc;
       continue;
     }
 #endif
     if (cg == 2) {
-      if (K <= 20) rc = launch_tc<20, LRB_NS_PAIR, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
-      else if (K <= 32) rc = launch_tc<32, 4, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
-      else rc = launch_tc<50, 3, false, 2>(ta, tb2, tbias, p, d.grid, st, ov);
+      if (K <= 20) rc = launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20>(ta, tb2, tbias, p, d.grid, st, ov);
+      else if (K <= 32) rc = launch_tc<32, 4, false, 2, 8>(ta, tb2, tbias, p, d.grid, st, ov);
+      else rc = launch_tc<50, 3, false, 2, 8>(ta, tb2, tbias, p, d.grid, st, ov);
     } else {
-      if (K <= 20) rc = launch_tc<20, 3, false, 1>(ta, tb1, tbias, p, d.grid, st, ov);
-      else if (K <= 32) rc = launch_tc<32, 3, false, 1>(ta, tb1, tbias, p, d.grid, st, ov);
-      else rc = launch_tc<50, 2, false, 1>(ta, tb1, tbias, p, d.grid, st, ov);
+      if (K <= 20) rc = launch_tc<20, 2, false, 1, LRB_EW20>(ta, tb1, tbias, p, d.grid, st, ov);
+      else if (K <= 32) rc = launch_tc<32, 3, false, 1, 8>(ta, tb1, tbias, p, d.grid, st, ov);
+      else rc = launch_tc<50, 2, false, 1, 8>(ta, tb1, tbias, p, d.grid, st, ov);
     }
     if (rc != LRB_OK) return rc;
   }
@@ -589,7 +592,7 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
   p.gslots = nullptr; p.gstride = 0; p.pair_drain = 0; p.c_share = 0; p.scout_tiles = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
   p.dense_out = out; p.dense_ld = ld_out; p.probe_out = nullptr;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
-  return launch_tc<20, 3, true, 1>(ta, tb, tb, p, d.grid, st);
+  return launch_tc<20, 3, true, 1, 8>(ta, tb, tb, p, d.grid, st);
 }
 
 }  // extern "C"

@@ -29,13 +29,18 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = 128 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
-constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int ACC_STAGES = 2;               // two 256-column fp32 accumulators fill the SM's 512 TMEM columns
+constexpr int TMEM_COLS = ACC_STAGES * BN;
+constexpr int DONE_RING = 8;                // "tile computed" barriers (see the kernel); must exceed the TMA ring depth
+// Epilogue warps of the K <= 20 kernel: 8 (two 128-column parts per tile) or 16 (four 64-column parts).  Measured on
+// B200 (10M rows, 4096 users): 16 warps read the accumulators a little faster in isolation (tools/epi_probe: 702 vs 757
+// cycles per tile) but lose in the kernel (96 registers per thread, twice the per-thread candidate sets): 5.86 vs 5.25 ms.
+#ifndef LRB_EW20
+#define LRB_EW20 8
+#endif
+constexpr int SLOT_PARTS = LRB_EW20 / 4;    // partial-list / union-bound slots reserved per stream (>= column parts)
 
 struct ScoreParams {
   int B;             // real users (rows >= B of the padded user matrix are ignored)
@@ -51,15 +56,15 @@ struct ScoreParams {
   const uint32_t* excl_bloom;  // [B][4] 128-bit membership filter over (id & 127)
   int excl_stride;
   int* gslots;                 // [m_tiles*128][slots] ordered-int keys: each FULL-stream thread's c-th best
-                               // score so far (memset 0x80 = unset).  The 2*s_full full-stream slots of a
-                               // user all start at t = 0; with c * 2*s_full >= K the minimum over them is a
+                               // score so far (memset 0x80 = unset).  The PARTS*s_full full-stream slots of a
+                               // user all start at t = 0; with c * PARTS*s_full >= K the minimum over them is a
                                // valid lower bound on the user's K-th best (union bound), also used by the
                                // shared-stream CTAs, whose own slots are ignored (they may start late).
   int c_share;                 // c (1..MAX_C_SHARE); 0 disables the union bound
   int pair_drain;              // CTA pairs: a drain request is forwarded to the peer CTA (1) or stays local (0)
   int scout_tiles;             // T0: the last T0 tiles of every segment are first run in "scout" mode (no
                                // candidate handling, only group maxima) to seed the union bound; 0 = off
-  uint8_t* ring;               // [gridDim.x][EPI_THREADS][RING_GROUPS][RING_REC_BYTES] candidate rings
+  uint8_t* ring;               // [gridDim.x][epilogue threads][RING_GROUPS][RING_REC_BYTES] candidate rings
   float* part_scores;          // [B][slots][K]
   int* part_ids;               // [B][slots][K]
   int* part_cnt;               // [B][slots]   (zeroed by the host wrapper)
@@ -68,8 +73,8 @@ struct ScoreParams {
   float* dense_out;            // dense mode only: [B][dense_ld], columns < rows written
   long long dense_ld;
   long long* probe_out;        // developer harness only (else nullptr): per CTA {SM cycles, nanoseconds, cycles epilogue
-                               // warp 0 waited for accumulators, cycles the MMA thread waited for a free accumulator
-                               // stage, cycles it waited for TMA data, 0, 0, 0}
+                               // warp 0 waited for accumulators, cycles the MMA warp waited for its operands /
+                               // a free accumulator stage, 0, 0, 0, 0}
   // stream decomposition (host computed, see score_decompose())
   int s_full;        // number of full streams (each = m_tiles CTAs, one per user tile)
   int rem;           // CTAs in the shared stream
@@ -81,7 +86,7 @@ struct Segment {
   int m;      // user tile
   int n0;     // first item tile
   int n1;     // one past the last item tile
-  int slot;   // partial-list slot (before the x2 for the column half)
+  int slot;   // stream slot (partial-list slot = slot * SLOT_PARTS + column part)
 };
 
 // Deterministic walk over the segments owned by one CTA; every warp role runs the same walk.
@@ -322,14 +327,57 @@ __device__ __noinline__ float compact_ring(const float4* ring, int cnt, float ow
   return own_thr;
 }
 
+// Everything only the drain needs, kept out of the hot loop's registers: the struct lives in the thread's local
+// memory (its address is handed to the out-of-line drain_rings()), so that the filter loop holds little more than
+// its two TMEM load buffers, the ring cursor and the threshold.
+struct DrainState {
+  const float4* ring;
+  const int* excl;             // this row's sorted exclusion list in global memory (nullptr = none)
+  int* rowthr;                 // this row's shared threshold (generic pointer into shared memory)
+  int* gslot;                  // where this thread publishes its c-th best (nullptr = it does not)
+  uint32_t excl_s;             // shared-memory copy of the list (0 = none)
+  uint32_t bloom0, bloom1, bloom2, bloom3;
+  uint32_t ls, li, ln;
+  int excl_stride, K, limit_gid, c_share, published;
+  bool live;
+};
+
+// Lock-step drain of the warp's rings (compact_ring) + publication of the improved bounds.  Returns the thread's
+// own K-th best.
+template <int STRIDE, int KMAX>
+__device__ __noinline__ float drain_rings(DrainState* st, int cnt, float own_thr) {
+  float shared_thr = -INFINITY;
+  if (st->live) {
+    const int kk = *reinterpret_cast<volatile int*>(st->rowthr);
+    if (kk != INT_MIN) shared_thr = key_to_float(kk);
+  }
+  own_thr = compact_ring<STRIDE, KMAX>(st->ring, cnt, own_thr, shared_thr, st->limit_gid, st->ls, st->li, st->ln, st->K,
+                                       st->excl, st->excl_s, st->excl_stride, st->bloom0, st->bloom1, st->bloom2,
+                                       st->bloom3);
+  if (st->live) {
+    if (own_thr > -INFINITY) atomicMax(st->rowthr, float_to_key(own_thr));   // sibling column half
+    if (st->gslot != nullptr) {
+      const float cb = set_cth_best<STRIDE>(st->ls, st->ln, st->c_share);
+      const int key = float_to_key(cb);
+      if (cb > -INFINITY && key > st->published) {
+        st->published = key;
+        *st->gslot = key;   // monotone, single writer
+      }
+    }
+  }
+  return own_thr;
+}
+
 constexpr int EX_CAP = 56;   // ints per row of the shared-memory exclusion copy (L <= 54)
 constexpr int BIASBLK_BYTES = BN * 16 * 2;   // one tile of the folded-bias K=16 block (8 KB)
 constexpr int ONES_BYTES = BM * 16 * 2;      // the matching [128][16] "ones" A block (4 KB)
 
 // CG = CTAs per MMA (tcgen05 cta_group): with CG == 2 every CTA stages only its half of the item tile
 // (128 rows) and of the bias block; the pair's MMA reads both halves.
-template <int KMAX, int NS, int CG = 1>
+// EW = epilogue warps (8 or 16): warp w reads TMEM lanes 32*(w%4).. and column part w/4 of PARTS = EW/4.
+template <int KMAX, int NS, int CG, int EW>
 struct SmemLayout {
+  static constexpr int kEpiThreads = EW * 32;
   static constexpr bool kExclSmem = (KMAX <= 20);   // larger K variants have no room for it
   static constexpr int kBBytes = B_BYTES / CG;              // this CTA's part of the item tile
   static constexpr int kBiasBytes = BIASBLK_BYTES / CG;     // ... and of the folded-bias block
@@ -338,18 +386,19 @@ struct SmemLayout {
   static constexpr int kOnes = kA + A_BYTES;
   static constexpr int kB = kOnes + ONES_BYTES;            // 20 KB offset: 1024-aligned
   static constexpr int kListS = kB + NS * kStage;
-  static constexpr int kListI = kListS + KMAX * EPI_THREADS * 4;
-  static constexpr int kListN = kListI + KMAX * EPI_THREADS * 4;
-  static constexpr int kRowThr = kListN + EPI_THREADS * 8;
+  static constexpr int kListI = kListS + KMAX * kEpiThreads * 4;
+  static constexpr int kListN = kListI + KMAX * kEpiThreads * 4;
+  static constexpr int kRowThr = kListN + kEpiThreads * 8;
   static constexpr int kExcl = kRowThr + 2 * BM * 4 + 16;   // two threshold buffers + service-warp flags
   static constexpr int kBars = kExcl + (kExclSmem ? BM * EX_CAP * 4 : 0);
-  // barriers: full[NS], empty[NS], tmem_full[2], tmem_empty[2], a_full, a_empty
-  static constexpr int kNumBars = 2 * NS + 2 * ACC_STAGES + 2;
+  // barriers: full[NS], done[DONE_RING], tmem_empty[2], a_full, a_empty
+  static constexpr int kNumBars = NS + DONE_RING + ACC_STAGES + 2;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
   static constexpr int kAlloc = kTotal + 1024;  // slack for manual 1024-B alignment
   static_assert(kAlloc <= 232448, "shared memory budget exceeded");
   static_assert(kB % 1024 == 0 && kStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-B alignment");
+  static_assert(DONE_RING > NS, "the producer looks NS tiles back in the ring of 'tile computed' barriers");
 };
 
 // No-swizzle K-major canonical layout of a [rows][16] bf16 block (UMMA "INTERLEAVE"): 8x8 core
@@ -366,16 +415,33 @@ LRB_DEVINL uint64_t umma_desc_k16_nosw(uint32_t smem_addr) {
 
 // PROBE (developer harness only, tools/tc_check; the library instantiates PROBE == 0):
 //   1 = null epilogue (TMA + MMA only)            2 = TMA only (no MMA, null epilogue)
-//   3 = no TMA traffic after the ring is primed (MMA + full epilogue on resident operands)
-//   4 = no TMA traffic, null epilogue (MMA only)  5 = full pipeline, the filter never passes (threshold +inf)
-//   6 = the product path, timed.   Every probe writes per-CTA {cycles, ns} to p.probe_out.
-template <int KMAX, int NS, bool kDense, int CG, int PROBE = 0>
-__global__ void __launch_bounds__(THREADS, 1)
+//   4 = no TMA traffic after the ring is primed, null epilogue (MMA only)
+//   5 = full pipeline, the filter never passes (threshold +inf)     6 = the product path, timed.
+// Every probe writes per-CTA {cycles, ns, wait counters} to p.probe_out.
+//
+// Synchronisation (mbarriers; "tile" = one 256-item tile of one segment, counted per CTA in issue order):
+//   full[s]        TMA bytes of shared-memory stage s have landed            producer -> MMA warp
+//   done[t % 8]    the MMAs of tile t have completed (ONE tcgen05.commit per tile):
+//                  the accumulator stage t % 2 is full                       MMA -> epilogue warps (both CTAs of a pair)
+//                  AND shared-memory stage t % NS may be refilled            MMA -> TMA producer(s)
+//   tmem_empty[a]  every epilogue warp has read accumulator stage a          epilogue -> MMA warp
+// The MMA-issuing thread is the one serial resource of the pipeline: whatever it spends between two tiles that is
+// not `tcgen05.mma` shows up as idle tensor-pipe cycles (measured, tools/tmem_probe modes 8-10: a second commit per
+// tile costs 80-130 cycles, a second barrier wait ~120).  Hence one commit per tile, and the two things it has to
+// wait for (operands landed, accumulator stage drained) are polled by two lanes of the MMA warp in ONE try_wait.
+template <int KMAX, int NS, bool kDense, int CG, int EW, int PROBE = 0>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_bias, const ScoreParams p) {
-  using L = SmemLayout<KMAX, NS, CG>;
+  using L = SmemLayout<KMAX, NS, CG, EW>;
   static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
+  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+  constexpr int EPI_THREADS = EW * 32;
+  constexpr int PARTS = EW / 4;            // column parts of a tile
+  constexpr int COLS = BN / PARTS;         // columns per epilogue thread and tile (128 or 64)
+  constexpr int CH = COLS / 32;            // x32 TMEM loads per thread and tile (4 or 2)
+  static_assert(PARTS <= SLOT_PARTS, "slot stride too small");
   // CTA pair: cluster rank 0 leads (issues the MMAs, owns the barriers the pair synchronises on);
   // the pair walks the segments of "pair index" blockIdx.x / 2 and CTA `rank` owns user tile 2*m + rank.
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -395,10 +461,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   int* sExcl = reinterpret_cast<int*>(smem + L::kExcl);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + NS;
-  uint64_t* tmem_full_bar = bars + 2 * NS;
-  uint64_t* tmem_empty_bar = bars + 2 * NS + ACC_STAGES;
-  uint64_t* a_full_bar = bars + 2 * NS + 2 * ACC_STAGES;
+  uint64_t* done_bar = bars + NS;
+  uint64_t* tmem_empty_bar = bars + NS + DONE_RING;
+  uint64_t* a_full_bar = bars + NS + DONE_RING + ACC_STAGES;
   uint64_t* a_empty_bar = a_full_bar + 1;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
 
@@ -420,16 +485,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < ACC_STAGES; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], EPI_WARPS * CG);   // pair: both CTAs' epilogues arrive on the leader's
-    }
+    for (int i = 0; i < NS; ++i) mbar_init(&full_bar[i], 1);
+    for (int i = 0; i < DONE_RING; ++i) mbar_init(&done_bar[i], 1);
+    for (int i = 0; i < ACC_STAGES; ++i) mbar_init(&tmem_empty_bar[i], EW * CG);   // pair: both CTAs' epilogues arrive on the leader's
     mbar_init(a_full_bar, 1);
-    mbar_init(a_empty_bar, 1);
+    mbar_init(a_empty_bar, 2);   // one commit from each MMA-issuing warp
     mbar_fence_init();
     sSvc[0] = -1; sSvc[1] = -1; sSvc[2] = 0; sSvc[3] = 0;
   }
@@ -446,11 +506,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // "ones" block: column 0..2 = 1.0 (they multiply the hi/mid/lo bf16 terms of the bias)
     for (int i = lane; i < ONES_BYTES / 2; i += 32) {
       // canonical no-swizzle layout: element (row, k) at (row/8)*256 + (k/8)*128 + (row%8)*16 + (k%8)*2
-      const int grp = i >> 7;          // 128 elements per 8-row group (2 core matrices)
       const int rem = i & 127;
       const int khalf = rem >> 6;
       const int k = khalf * 8 + (rem & 7);
-      (void)grp;
       reinterpret_cast<__nv_bfloat16*>(sOnes)[i] = __float2bfloat16(k < 3 ? 1.0f : 0.0f);
     }
     // make the generic-proxy writes visible to the tensor core (async proxy)
@@ -470,8 +528,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int stage = 0;
       uint32_t phase = 0;
       int seg_idx = 0;
-      int probe_tiles = 0;
-      (void)probe_tiles;
+      int t = 0;                      // tiles issued so far (all segments, scout tiles included)
       // bytes the (leader's) full barrier expects per stage: the parts of both CTAs
       const uint32_t stage_tx = (L::kBBytes + (has_bias ? L::kBiasBytes : 0)) * CG;
       const uint32_t a_full_lead = CG == 2 ? mapa_u32(smem_u32(a_full_bar), 0) : 0u;
@@ -486,13 +543,13 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tma_load_2d(sA, &tmap_a, a_full_bar, 0, m_own * BM);
         }
         const int n_scout = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
-        for (int it = -n_scout; it < sg.n1 - sg.n0; ++it) {
+        for (int it = -n_scout; it < sg.n1 - sg.n0; ++it, ++t) {
           const int n = it < 0 ? sg.n1 + it : sg.n0 + it;   // scout pass re-visits the segment's last tiles
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if ((PROBE == 3 || PROBE == 4) && ++probe_tiles > NS) {
+          // stage t % NS was last read by the MMAs of tile t - NS
+          if (t >= NS) mbar_wait(&done_bar[(t - NS) % DONE_RING], ((t - NS) / DONE_RING) & 1);
+          if (PROBE == 4 && t >= NS) {
             // probe: the stage still holds an item tile -- hand it to the MMA again, no TMA traffic
-            if (CG == 2) { if (cta_rank == 0) mbar_arrive(&full_bar[stage]); }
-            else mbar_arrive(&full_bar[stage]);
+            if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -518,67 +575,74 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         ++seg_idx;
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers =====================
+    // TWO issuing warps, one per accumulator stage: warp 1 takes the even tiles, warp 2 the odd ones.  An issuing
+    // thread is blocked in `tcgen05.mma` while the tensor pipe is busy and only then gets to its commit, its next
+    // barrier waits and its descriptor arithmetic -- with a single issuer that gap (~150 cycles per tile) was idle
+    // tensor-pipe time (MMA-only probe: 665-685 cycles per tile against 512 for back-to-back MMAs); with two, one
+    // warp's gap hides behind the other's MMAs.  In each warp lane 0 polls "operands landed" and lane 1
+    // "accumulator stage drained" with ONE try_wait instruction; lane 0 issues.
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+      const int mw = warp - 1;        // == the accumulator stage this warp owns
       SegmentWalk walk(p, walk_id);
       Segment sg;
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
       int seg_idx = 0;
+      int t = 0;
       const uint64_t desc_a0 = umma_desc_k_sw128(smem_u32(sA));
       const uint64_t desc_ones = umma_desc_k16_nosw(smem_u32(sOnes));
-      long long probe_wait_empty = 0, probe_wait_full = 0;
+      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(mw * BN);
+      long long probe_wait = 0;
       while (walk.next(sg)) {
-        mbar_wait(a_full_bar, seg_idx & 1);
+        if (lane == 0) mbar_wait(a_full_bar, seg_idx & 1);
+        __syncwarp();
         const int n_scout = (kDense || p.scout_tiles <= 0) ? 0 : min(p.scout_tiles, sg.n1 - sg.n0);
-        for (int it = -n_scout; it < sg.n1 - sg.n0; ++it) {
-          if (PROBE != 0) {
-            const long long w0 = clock64();
-            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-            const long long w1 = clock64();
-            mbar_wait(&full_bar[stage], phase);
-            probe_wait_empty += w1 - w0;
-            probe_wait_full += clock64() - w1;
-          } else {
-            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-            mbar_wait(&full_bar[stage], phase);
+        const int t_end = t + n_scout + (sg.n1 - sg.n0);
+        for (t += (t & 1) ^ mw; t < t_end; t += 2) {   // this warp's tiles of the segment
+          const int stage = t % NS;
+          {
+            const long long w0 = PROBE != 0 ? clock64() : 0;
+            if (lane < 2) {
+              uint64_t* bar = lane == 0 ? &full_bar[stage] : &tmem_empty_bar[mw];
+              const uint32_t par = lane == 0 ? static_cast<uint32_t>((t / NS) & 1) : static_cast<uint32_t>(((t >> 1) & 1) ^ 1);
+              mbar_wait(bar, par);
+            }
+            __syncwarp();
+            if (PROBE != 0) probe_wait += clock64() - w0;
           }
-          tc_fence_after();
-          const uint32_t st = smem_u32(sB + stage * L::kStage);
-          const uint64_t desc_b0 = umma_desc_k_sw128(st);
-          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * BN);
-          if (PROBE != 2)
+          if (lane == 0) {
+            tc_fence_after();
+            const uint32_t st = smem_u32(sB + stage * L::kStage);
+            const uint64_t desc_b0 = umma_desc_k_sw128(st);
+            if (PROBE != 2) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the 128-B swizzle atom: +2 in 16-B units
-            if (CG == 2) umma_bf16_ss_pair(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
-            else umma_bf16_ss(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                // advance 32 bytes (16 bf16) along K inside the 128-B swizzle atom: +2 in 16-B units
+                if (CG == 2) umma_bf16_ss_pair(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+                else umma_bf16_ss(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+              }
+              // folded bias: D += ones[128x16] * bias_blk[256x16]^T  (hi + mid + lo bf16 terms)
+              if (has_bias) {
+                if (CG == 2) umma_bf16_ss_pair(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
+                else umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
+              }
+            }
+            // ONE commit: "tile t computed" = accumulator full (epilogues) + shared-memory stage free (producers)
+            if (CG == 2) umma_commit_pair(&done_bar[t % DONE_RING], 0b11);
+            else umma_commit(&done_bar[t % DONE_RING]);
           }
-          // folded bias: D += ones[128x16] * bias_blk[256x16]^T  (hi + mid + lo bf16 terms)
-          if (has_bias && PROBE != 2) {
-            if (CG == 2) umma_bf16_ss_pair(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
-            else umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
-          }
-          if (CG == 2) {
-            umma_commit_pair(&empty_bar[stage], 0b11);
-            umma_commit_pair(&tmem_full_bar[acc], 0b11);
-          } else {
-            umma_commit(&empty_bar[stage]);
-            umma_commit(&tmem_full_bar[acc]);
-          }
-          if (++stage == NS) { stage = 0; phase ^= 1; }
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          __syncwarp();
         }
-        if (CG == 2) umma_commit_pair(a_empty_bar, 0b11);
-        else umma_commit(a_empty_bar);
+        t = t_end;
+        if (lane == 0) {   // this warp's MMAs on the segment's user tile are done (the barrier counts both warps)
+          if (CG == 2) umma_commit_pair(a_empty_bar, 0b11);
+          else umma_commit(a_empty_bar);
+        }
+        __syncwarp();
         ++seg_idx;
       }
-      if (PROBE != 0 && p.probe_out != nullptr) {
-        p.probe_out[blockIdx.x * 8 + 3] = probe_wait_empty;
-        p.probe_out[blockIdx.x * 8 + 4] = probe_wait_full;
-      }
+      if (PROBE != 0 && lane == 0 && warp == 1 && p.probe_out != nullptr) p.probe_out[blockIdx.x * 8 + 3] = probe_wait;
     }
   } else if (warp == 3) {
     // ===================== threshold service =====================
@@ -596,9 +660,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (b >= p.B) continue;
             const volatile int* gs = p.gslots + static_cast<size_t>(b) * p.gstride;
             int mn = INT_MAX;
-            for (int sl = 0; sl < 2 * p.s_full; ++sl) {
-              const int v = gs[sl];
-              mn = v < mn ? v : mn;
+            for (int sl = 0; sl < p.s_full; ++sl) {
+#pragma unroll
+              for (int pt = 0; pt < PARTS; ++pt) {
+                const int v = gs[sl * SLOT_PARTS + pt];
+                mn = v < mn ? v : mn;
+              }
             }
             if (mn > static_cast<int>(0x80808080) && sSvc[1] == seg) atomicMax(&sRowThr[(seg & 1) * BM + rr], mn);
           }
@@ -608,10 +675,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;          // 0..7
+    const int ew = warp - 4;          // 0..EW-1
     const int quad = ew & 3;          // TMEM lane quadrant == warp % 4
-    const int half = ew >> 2;         // column half of the tile
-    const int et = ew * 32 + lane;    // epilogue thread index 0..255
+    const int part = ew >> 2;         // column part of the tile
+    const int et = ew * 32 + lane;    // epilogue thread index
     const int r = quad * 32 + lane;   // row inside the user tile
     const uint32_t ls = smem_u32(sListS + et);
     const uint32_t li = smem_u32(sListI + et);
@@ -619,18 +686,32 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     SegmentWalk walk(p, walk_id);
     Segment sg;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int t = 0;                        // tiles consumed so far (same count as the MMA warp's)
     int seg_idx = -1;
-    long long probe_epi_wait = 0;
+    long long probe_epi_wait = 0, probe_drain_cyc = 0, probe_drains = 0, probe_appends = 0;
     // "accumulator stage drained": local barrier, or the leader's for a CTA pair
     const uint32_t acc_empty_addr0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
-    auto release_acc = [&](int a) {   // (consecutive mbarriers are 8 bytes apart, in either address window)
-      if (CG == 2) mbar_arrive_cluster(acc_empty_addr0 + static_cast<uint32_t>(a) * 8u);
-      else mbar_arrive(&tmem_empty_bar[a]);
-    };
     const uint32_t peer_drain_addr =
         CG == 2 ? mapa_u32(smem_u32(const_cast<int*>(&sSvc[3])), cta_rank ^ 1u) : 0u;
+    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(part * COLS);
+    auto wait_tile = [&]() {   // the accumulator of tile t is complete
+      if (PROBE != 0) {
+        const long long w0 = clock64();
+        mbar_wait(&done_bar[t % DONE_RING], (t / DONE_RING) & 1);
+        probe_epi_wait += clock64() - w0;
+      } else {
+        mbar_wait(&done_bar[t % DONE_RING], (t / DONE_RING) & 1);
+      }
+      tc_fence_after();
+    };
+    auto release_tile = [&]() {   // every load of tile t's accumulator has landed in this warp's registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {            // (consecutive mbarriers are 8 bytes apart, in either address window)
+        if (CG == 2) mbar_arrive_cluster(acc_empty_addr0 + static_cast<uint32_t>(t % ACC_STAGES) * 8u);
+        else mbar_arrive(&tmem_empty_bar[t % ACC_STAGES]);
+      }
+    };
     while (walk.next(sg)) {
       ++seg_idx;
       const int m_own = CG == 2 ? sg.m * 2 + static_cast<int>(cta_rank) : sg.m;
@@ -641,8 +722,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       sts_s32(ln, 0);
       float own_thr = -INFINITY;
       int published = INT_MIN;
-      if (half == 0) rowthr[r] = INT_MIN;
-      const int my_slot = sg.slot * 2 + half;
+      if (part == 0) rowthr[r] = INT_MIN;
+      const int my_slot = sg.slot * SLOT_PARTS + part;
       const bool publishes = sg.slot < p.s_full;   // only full-stream threads feed the union bound
       const int* excl = nullptr;
       uint32_t bloom0 = 0u, bloom1 = 0u, bloom2 = 0u, bloom3 = 0u;
@@ -686,35 +767,30 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float tm[MAX_C_SHARE];   // the MAX_C_SHARE largest group maxima, descending
 #pragma unroll
         for (int j = 0; j < MAX_C_SHARE; ++j) tm[j] = -INFINITY;
-        for (int it = 0; it < n_scout_run; ++it) {
-          mbar_wait(&tmem_full_bar[acc], acc_phase);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                 static_cast<uint32_t>(acc * BN + half * (BN / 2));
+        for (int it = 0; it < n_scout_run; ++it, ++t) {
+          wait_tile();
+          if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
+            release_tile();
+            continue;
+          }
           // Columns past the end of the table (the ragged last tile) must not count as admissible items:
           // without a folded-bias block they score exactly 0 (TMA zero-fills out-of-bounds rows), and a
           // bound published from them could exceed a user's true K-th best.  valid = real columns of
-          // this thread's 128-column half in this tile (warp-uniform; < 128 only for the last tile).
-          const int valid = p.rows - ((sg.n1 - n_scout_run + it) * BN + half * (BN / 2));
-          if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release_acc(acc);
-            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-            continue;
-          }
+          // this thread's COLS-column part in this tile (warp-uniform; < COLS only for the last tile).
+          const int valid = p.rows - ((sg.n1 - n_scout_run + it) * BN + part * COLS);
+          const uint32_t taddr = taddr_lane + static_cast<uint32_t>((t % ACC_STAGES) * BN);
           uint32_t w[2][32];
           tmem_ld_32x32(taddr, w[0]);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < 3) tmem_ld_32x32(taddr + (c + 1) * 32, w[(c + 1) & 1]);
+          for (int c = 0; c < CH; ++c) {
+            if (c < CH - 1) tmem_ld_32x32(taddr + (c + 1) * 32, w[(c + 1) & 1]);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               float q[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(w[c & 1][g * 16 + j]);
-              if (valid < BN / 2) {
+              if (valid < COLS) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) q[j] = (c * 32 + g * 16 + j < valid) ? q[j] : -INFINITY;
               }
@@ -731,15 +807,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tm[j] = hi;
               }
             }
-            if (c < 3) tmem_ld_wait();
+            if (c < CH - 1) tmem_ld_wait();
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(acc);
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          release_tile();
         }
         if (live && publishes && n_scout > 0) {
-          // E = excluded ids that fall inside the scouted id range (either column half)
+          // E = excluded ids that fall inside the scouted id range (any column part)
           int E = 0;
           if (excl != nullptr) {
             const int g_lo = p.row_offset + (sg.n1 - n_scout_run) * BN;
@@ -761,6 +834,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         boot = false;
         // give the threshold service a bounded moment to pick the bound up (never blocks on other CTAs)
+#pragma unroll 1
         for (int spin = 0; spin < 40; ++spin) {
           const int kk = *reinterpret_cast<volatile int*>(rowthr + r);
           if (__all_sync(0xffffffffu, kk != INT_MIN || !live)) break;
@@ -771,32 +845,63 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           p.ring + (static_cast<size_t>(blockIdx.x) * EPI_THREADS + et) * (RING_GROUPS * RING_REC_BYTES));
       const int limit_gid = p.row_offset + p.rows;
 
-      // lock-step drain of the warp's rings + publication of the improved bounds
+      // lock-step drain of the warp's rings + publication of the improved bounds (out of line, state in local memory)
+      DrainState dst;
+      dst.ring = ring; dst.excl = excl; dst.rowthr = rowthr + r;
+      dst.gslot = (live && p.c_share > 0 && publishes) ? p.gslots + static_cast<size_t>(b) * p.gstride + my_slot : nullptr;
+      dst.excl_s = excl_s; dst.bloom0 = bloom0; dst.bloom1 = bloom1; dst.bloom2 = bloom2; dst.bloom3 = bloom3;
+      dst.ls = ls; dst.li = li; dst.ln = ln;
+      dst.excl_stride = p.excl_stride; dst.K = p.K; dst.limit_gid = limit_gid; dst.c_share = p.c_share;
+      dst.published = published; dst.live = live;
       auto drain = [&]() {
-        float shared_thr = -INFINITY;
-        if (live) {
-          const int kk = *reinterpret_cast<volatile int*>(rowthr + r);
-          if (kk != INT_MIN) shared_thr = key_to_float(kk);
+        if (PROBE != 0) {
+          const long long d0 = clock64();
+          probe_appends += cnt;
+          own_thr = drain_rings<EPI_THREADS, KMAX>(&dst, cnt, own_thr);
+          probe_drain_cyc += clock64() - d0;
+          probe_drains += 1;
+        } else {
+          own_thr = drain_rings<EPI_THREADS, KMAX>(&dst, cnt, own_thr);
         }
-        own_thr = compact_ring<EPI_THREADS, KMAX>(ring, cnt, own_thr, shared_thr, limit_gid, ls, li, ln, p.K, excl,
-                                            excl_s, p.excl_stride, bloom0, bloom1, bloom2, bloom3);
         cnt = 0;
-        if (live) {
-          if (own_thr > -INFINITY) atomicMax(&rowthr[r], float_to_key(own_thr));   // sibling column half
-          if (p.c_share > 0 && publishes) {
-            const float cb = set_cth_best<EPI_THREADS>(ls, ln, p.c_share);
-            const int key = float_to_key(cb);
-            if (cb > -INFINITY && key > published) {
-              published = key;
-              p.gslots[static_cast<size_t>(b) * p.gstride + my_slot] = key;   // monotone, single writer
+      };
+
+      const uint32_t rowthr_s = smem_u32(rowthr + r);
+      const uint32_t drain_seq_s = smem_u32(const_cast<int*>(&sSvc[3]));
+
+      // hot path per 32 columns: two FMNMX3 trees, ONE compare against the thread's threshold; a group whose
+      // maximum passes is not inspected, it is dumped into the thread's ring (5 stores)
+      auto filter_chunk = [&](const uint32_t (&x)[32], float t_eff, int gid0) {
+        float gmax[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float qv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) qv[j] = __uint_as_float(x[g * 16 + j]);
+          const float m1 = max3(qv[0], qv[1], qv[2]);
+          const float m2 = max3(qv[3], qv[4], qv[5]);
+          const float m3 = max3(qv[6], qv[7], qv[8]);
+          const float m4 = max3(qv[9], qv[10], qv[11]);
+          const float m5 = max3(qv[12], qv[13], qv[14]);
+          gmax[g] = fmaxf(max3(m1, m2, m3), max3(m4, m5, qv[15]));
+        }
+        if (fmaxf(gmax[0], gmax[1]) >= t_eff) {   // one branch per 32 columns; the group split happens inside it
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (gmax[g] >= t_eff) {
+              float4* rec = ring + cnt * (RING_REC_BYTES / 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                rec[j] = make_float4(__uint_as_float(x[g * 16 + 4 * j]), __uint_as_float(x[g * 16 + 4 * j + 1]),
+                                     __uint_as_float(x[g * 16 + 4 * j + 2]), __uint_as_float(x[g * 16 + 4 * j + 3]));
+              reinterpret_cast<int*>(rec + 4)[0] = gid0 + g * 16;
+              ++cnt;
             }
           }
         }
       };
 
-      const uint32_t rowthr_s = smem_u32(rowthr + r);
-      const uint32_t drain_seq_s = smem_u32(const_cast<int*>(&sSvc[3]));
-      for (int n = sg.n0; n < sg.n1; ++n) {
+      for (int n = sg.n0; n < sg.n1; ++n, ++t) {
         // rows beyond B never produce candidates: their threshold is +inf.  The row's shared threshold is
         // read (shared-space load, issued before the wait so that its latency hides behind it) once per tile.
         float t_eff = live ? own_thr : INFINITY;
@@ -805,99 +910,74 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (kk != INT_MIN) t_eff = fmaxf(own_thr, key_to_float(kk));
         }
         if (PROBE == 5) t_eff = INFINITY;
-        if (PROBE != 0) {
-          const long long w0 = clock64();
-          mbar_wait(&tmem_full_bar[acc], acc_phase);
-          probe_epi_wait += clock64() - w0;
-        } else {
-          mbar_wait(&tmem_full_bar[acc], acc_phase);
-        }
-        tc_fence_after();
+        wait_tile();
         if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(acc);
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          release_tile();
           continue;
         }
+        const uint32_t taddr = taddr_lane + static_cast<uint32_t>((t % ACC_STAGES) * BN);
+        const int col_gid0 = p.row_offset + n * BN + part * COLS;
 
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(acc * BN + half * (BN / 2));
-        const int col_gid0 = p.row_offset + n * BN + half * (BN / 2);
-
-        uint32_t v[2][32];
-        tmem_ld_32x32(taddr, v[0]);
-        tmem_ld_wait();
+        if (kDense) {
+          uint32_t v[2][32];
+          tmem_ld_32x32(taddr, v[0]);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < 3) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-          float s[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[c & 1][j]);
-          if (kDense) {
+          for (int c = 0; c < CH; ++c) {
+            if (c < CH - 1) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
             const int row = m_own * BM + r;
-            const int col0 = n * BN + half * (BN / 2) + c * 32;
+            const int col0 = n * BN + part * COLS + c * 32;
             if (row < p.B) {
-              float* dst = p.dense_out + static_cast<size_t>(row) * p.dense_ld + col0;
+              float* dstp = p.dense_out + static_cast<size_t>(row) * p.dense_ld + col0;
               if (col0 + 32 <= p.rows && (p.dense_ld & 3) == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  reinterpret_cast<float4*>(dst)[j] =
-                      make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+                  reinterpret_cast<float4*>(dstp)[j] =
+                      make_float4(__uint_as_float(v[c & 1][4 * j]), __uint_as_float(v[c & 1][4 * j + 1]),
+                                  __uint_as_float(v[c & 1][4 * j + 2]), __uint_as_float(v[c & 1][4 * j + 3]));
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.rows) dst[j] = s[j];
+                  if (col0 + j < p.rows) dstp[j] = __uint_as_float(v[c & 1][j]);
               }
             }
-          } else {
-            float gmax[2];
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const float* q = s + g * 16;
-              const float m1 = max3(q[0], q[1], q[2]);
-              const float m2 = max3(q[3], q[4], q[5]);
-              const float m3 = max3(q[6], q[7], q[8]);
-              const float m4 = max3(q[9], q[10], q[11]);
-              const float m5 = max3(q[12], q[13], q[14]);
-              const float m6 = max3(m1, m2, m3);
-              const float m7 = max3(m4, m5, q[15]);
-              gmax[g] = fmaxf(m6, m7);
-            }
-            // one branch per 32 columns on the hot path; the group split happens inside it
-            if (fmaxf(gmax[0], gmax[1]) >= t_eff) {
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                if (gmax[g] >= t_eff) {
-                  const float* q = s + g * 16;
-                  float4* rec = ring + cnt * (RING_REC_BYTES / 16);
-                  rec[0] = make_float4(q[0], q[1], q[2], q[3]);
-                  rec[1] = make_float4(q[4], q[5], q[6], q[7]);
-                  rec[2] = make_float4(q[8], q[9], q[10], q[11]);
-                  rec[3] = make_float4(q[12], q[13], q[14], q[15]);
-                  reinterpret_cast<int*>(rec + 4)[0] = col_gid0 + c * 32 + g * 16;
-                  ++cnt;
-                }
-              }
-            }
+            if (c < CH - 1) tmem_ld_wait();
           }
-          if (c < 3) tmem_ld_wait();
-          if (c == 2) {
-            // all four TMEM loads of this accumulator stage have landed in registers:
-            // hand the stage back to the MMA warp before chewing on the last chunk.
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release_acc(acc);
+          release_tile();
+          continue;
+        }
+
+        uint32_t v[2][32];
+        if (CH == 2) {
+          // 16 epilogue warps: this thread's 64 columns arrive with two loads issued together; the stage goes
+          // back to the MMA warp before anything is computed -- the other three warps of the SM sub-partition
+          // keep the TMEM read path busy meanwhile
+          tmem_ld_32x32(taddr, v[0]);
+          tmem_ld_32x32(taddr + 32, v[1]);
+          tmem_ld_wait();
+          release_tile();
+          filter_chunk(v[0], t_eff, col_gid0);
+          filter_chunk(v[1], t_eff, col_gid0 + 32);
+        } else {
+          // 8 epilogue warps: four loads, software pipelined one chunk ahead
+          tmem_ld_32x32(taddr, v[0]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if (c < CH - 1) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+            filter_chunk(v[c & 1], t_eff, col_gid0 + c * 32);
+            if (c < CH - 1) tmem_ld_wait();
+            if (c == CH - 2) release_tile();   // all loads of this stage have landed: hand it back early
           }
         }
-        if (!kDense) {
-          // uniform point, once per tile: a tile adds at most 8 records per thread, so draining
+        {
+          // uniform point, once per tile: a tile adds at most COLS/16 <= 8 records per thread, so draining
           // whenever some lane holds more than RING_GROUPS-8 keeps every ring within capacity.
           // The first tile of a segment always drains (bootstrap): every stream then holds K entries
           // and publishes its c-th best within the first microseconds, which defines the union bound.
-          // Drains are synchronised across the CTA's eight epilogue warps: a warp that must drain bumps a
+          // Drains are synchronised across the CTA's epilogue warps: a warp that must drain bumps a
           // shared sequence number and every warp drains at its next tile boundary.  A drain stalls the
-          // two-deep accumulator ring for everybody, so eight simultaneous drains cost one stall, not eight.
+          // two-deep accumulator ring for everybody, so simultaneous drains cost one stall, not EW.
           const bool need = __any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0));
           int seq = lds_volatile_s32(drain_seq_s);
           if (need && seq == drain_seen) {
@@ -914,14 +994,13 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             drain();
           }
         }
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
 
       if (!kDense) drain();   // final drain of this segment (whole warp, lock-step)
 
       if (!kDense && live) {
         const int held = lds_s32(ln);
-        const size_t base = (static_cast<size_t>(b) * p.slots + (sg.slot * 2 + half));
+        const size_t base = (static_cast<size_t>(b) * p.slots + my_slot);
         p.part_cnt[base] = held;
         for (int i = 0; i < held; ++i) {
           p.part_scores[base * p.K + i] = lds_f32(ls + i * EPI_THREADS * 4);
@@ -931,7 +1010,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));  // before the next segment resets its buffer
     }
     if (et == 0) sSvc[2] = 1;   // all segments of this CTA are done: stop the threshold service
-    if (PROBE != 0 && et == 0 && p.probe_out != nullptr) p.probe_out[blockIdx.x * 8 + 2] = probe_epi_wait;
+    if (PROBE != 0 && et == 0 && p.probe_out != nullptr) {
+      p.probe_out[blockIdx.x * 8 + 2] = probe_epi_wait;
+      p.probe_out[blockIdx.x * 8 + 5] = probe_drain_cyc;
+      p.probe_out[blockIdx.x * 8 + 6] = probe_drains;
+      p.probe_out[blockIdx.x * 8 + 7] = probe_appends;
+    }
   }
 
   if (PROBE != 0 && threadIdx.x == 0 && p.probe_out != nullptr) {

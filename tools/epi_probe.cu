@@ -226,10 +226,12 @@ probe_kernel(int tiles, long long* cycles, unsigned* sink, float thr_in, float4*
       if (++acc == ACC) { acc = 0; ph ^= 1; }
     }
     if (cnt == 0x7fffffff) sink[0] = cnt;
+    // (taken by a thread that really waited for the last tile: BAR.SYNC is deferred-blocking, a clock read right
+    // after __syncthreads() by an idle warp returns the time the barrier was ISSUED)
+    if (threadIdx.x == 128) cycles[blockIdx.x] = clock64() - t0;
   }
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, ACC * BN); }
 }
 

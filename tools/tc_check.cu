@@ -323,15 +323,16 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
     lrb_debug_set_probe_out(nullptr);
     std::vector<long long> st(sms * 8);
     CK(cudaMemcpy(st.data(), dprobe, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    double cyc = 0, ns = 0, ew = 0, me = 0, mf = 0; int n = 0, nl = 0;
+    double cyc = 0, ns = 0, ew = 0, me = 0, dc = 0, dn = 0, ap = 0; int n = 0, nl = 0;
     for (int c = 0; c < sms; ++c) if (st[c * 8] > 0) {
-      cyc += st[c * 8]; ns += st[c * 8 + 1]; ew += st[c * 8 + 2]; ++n;
-      if (st[c * 8 + 3] + st[c * 8 + 4] > 0) { me += st[c * 8 + 3]; mf += st[c * 8 + 4]; ++nl; }
+      cyc += st[c * 8]; ns += st[c * 8 + 1]; ew += st[c * 8 + 2]; dc += st[c * 8 + 5]; dn += st[c * 8 + 6]; ap += st[c * 8 + 7]; ++n;
+      if (st[c * 8 + 3] > 0) { me += st[c * 8 + 3]; ++nl; }
     }
     if (n > 0)
-      printf("  per CTA: %.3f Mcycles in %.3f ms => SM clock %.0f MHz | epilogue warp 0 waited %.3f Mcycles for "
-             "accumulators | MMA thread waited %.3f Mcycles for a free accumulator stage, %.3f for TMA data\n",
-             cyc / n / 1e6, ns / n / 1e6, cyc / ns * 1e3, ew / n / 1e6, nl ? me / nl / 1e6 : 0.0, nl ? mf / nl / 1e6 : 0.0);
+      printf("  per CTA: %.3f Mcycles in %.3f ms => SM clock %.0f MHz | epilogue warp 0: waited %.3f Mcycles for accumulators, "
+             "%.1f drains taking %.3f Mcycles, thread 0 appended %.1f records | MMA warp 1 waited %.3f Mcycles for operands / "
+             "a free accumulator stage\n",
+             cyc / n / 1e6, ns / n / 1e6, cyc / ns * 1e3, ew / n / 1e6, dn / n, dc / n / 1e6, ap / n, nl ? me / nl / 1e6 : 0.0);
     cudaFree(dprobe);
   }
   double tflops = 2.0 * B * (double)rows * 64 / (ms * 1e-3) / 1e12;

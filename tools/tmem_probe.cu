@@ -44,7 +44,7 @@ LRB_DEVINL void tmem_ld_32x32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
 
 template <int EPI_WARPS, bool PAIRBUF>
 __global__ void __launch_bounds__(128 + EPI_WARPS * 32, 1)
-probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) {
+probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr, int random_data, int n128) {
   constexpr int THREADS = 128 + EPI_WARPS * 32;
   constexpr int PARTS = EPI_WARPS / 4;          // column parts per lane quadrant
   constexpr int COLS = BN / PARTS;              // columns per epilogue thread
@@ -54,15 +54,28 @@ probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) 
   uint8_t* sA = smem;                        // [128][64] bf16, 128-byte swizzle atoms (contents irrelevant)
   uint8_t* sB = smem + BM * BK * 2;          // [256][64] bf16
   __shared__ uint64_t full_bar[ACC], empty_bar[ACC];
+  __shared__ uint64_t sfull[4], sempty[4];      // modes 8-10: the scoring kernel's shared-memory stage handshake
   __shared__ uint32_t tmem_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool mma_on = mode <= 2 || mode >= 5;
+  const int extra = mode >= 8 ? mode - 7 : 0;   // 1: second commit per tile (nobody waits), 2: + wait on a stage barrier
+                                                // re-armed by a producer thread, 3: the same with clock64 reads around the waits
+  if (mode >= 8) mode = 0;
   const int ld_mode = mode == 0 ? 0 : (PAIRBUF ? 3 : ((mode == 1 || mode == 3 || mode >= 5) ? 1 : 2));
   const bool filter = mode >= 5;
-  for (int i = threadIdx.x; i < (BM + BN) * BK * 2 / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < (BM + BN) * BK * 2 / 4; i += THREADS) {
+    uint32_t v = 0x3c003c00u;
+    if (random_data) {   // pseudo-random bf16 pairs in (-2, 2): realistic operand toggling (tensor-core power)
+      uint32_t h = (i + 1u) * 2654435761u + blockIdx.x * 40503u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      v = (h & 0x807f807fu) | 0x3f003f00u | ((h >> 3) & 0x00800080u);
+    }
+    reinterpret_cast<uint32_t*>(smem)[i] = v;
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int i = 0; i < ACC; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], EPI_WARPS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 1); }
     mbar_fence_init();
   }
   if (warp == 2) { tmem_alloc(&tmem_ptr, ACC * BN); tmem_relinquish(); }
@@ -76,19 +89,46 @@ probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) 
   }
   const long long t0 = clock64();
   if (warp == 1 && lane == 0) {
-    uint32_t idesc = umma_idesc_bf16(BM, BN);
+    uint32_t idesc = umma_idesc_bf16(BM, n128 ? 128 : BN);
     if (ld_mode == 2) idesc &= ~(3u << 4);                 // c_format = F16 accumulators
     const uint64_t da = umma_desc_k_sw128(smem_u32(sA)), db = umma_desc_k_sw128(smem_u32(sB));
     int acc = 0; uint32_t ph = 0;
+    int stg = 0; uint32_t sph = 0;
+    long long wsum = 0;
     for (int t = 0; t < tiles; ++t) {
+      if (extra >= 2) {
+        const long long w0 = extra >= 3 ? clock64() : 0;
+        mbar_wait(&sfull[stg], sph);
+        if (extra >= 3) wsum += clock64() - w0;
+      }
       mbar_wait(&empty_bar[acc], ph ^ 1);
       tc_fence_after();
       if (mma_on) {
+        if (n128) {   // the same tile as two N = 128 halves (8 MMAs)
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(tmem_base + acc * BN, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : 0u);
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss(tmem_base + acc * BN + hh * 128, da + 2 * k, db + hh * 1024 + 2 * k, idesc, k > 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(tmem_base + acc * BN, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : 0u);
+        }
       }
       umma_commit(&full_bar[acc]);
+      if (extra >= 1) {
+        umma_commit(&sempty[stg]);
+        if (++stg == 3) { stg = 0; sph ^= 1; }
+      }
       if (++acc == ACC) { acc = 0; ph ^= 1; }
+    }
+    if (wsum == 0x7fffffff) sink[0] = 1;
+  } else if (warp == 0 && lane == 0 && extra >= 2) {
+    int stg = 0; uint32_t sph = 0;
+    for (int t = 0; t < tiles; ++t) {      // "producer": stage free -> hand it over again
+      mbar_wait(&sempty[stg], sph ^ 1);
+      mbar_arrive(&sfull[stg]);
+      if (++stg == 3) { stg = 0; sph ^= 1; }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4, quad = ew & 3, half = ew >> 2;
@@ -163,19 +203,22 @@ probe_kernel(int tiles, int mode, long long* cycles, unsigned* sink, float thr) 
       if (++acc == ACC) { acc = 0; ph ^= 1; }
     }
     if (x == 0x12345678u || hits == 0x7fffffff) sink[0] = x + hits;
+    // (taken by a thread that really waited for the last tile: BAR.SYNC is deferred-blocking, a clock read right
+    // after __syncthreads() by an idle warp returns the time the barrier was ISSUED)
+    if (threadIdx.x == 128) cycles[blockIdx.x] = clock64() - t0;
   }
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, ACC * BN); }
 }
 
+static int g_random = 0, g_n128 = 0;
 template <int EPI_WARPS, bool PAIRBUF = false>
 static double run(int sms, int tiles, int mode, long long* d_cycles, unsigned* d_sink) {
   const int smem = (BM + BN) * BK * 2 + 1024;
   cudaFuncSetAttribute(probe_kernel<EPI_WARPS, PAIRBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int rep = 0; rep < 2; ++rep) {
-    probe_kernel<EPI_WARPS, PAIRBUF><<<sms, 128 + EPI_WARPS * 32, smem>>>(tiles, mode, d_cycles, d_sink, 1e30f);
+    probe_kernel<EPI_WARPS, PAIRBUF><<<sms, 128 + EPI_WARPS * 32, smem>>>(tiles, mode, d_cycles, d_sink, 1e30f, g_random, g_n128);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); exit(1); }
   }
@@ -188,12 +231,20 @@ static double run(int sms, int tiles, int mode, long long* d_cycles, unsigned* d
 
 int main(int argc, char** argv) {
   const int tiles = argc > 1 ? atoi(argv[1]) : 4000;
-  const bool try_f16 = argc > 2;
+  const bool try_f16 = false;
+  g_random = argc > 2 ? atoi(argv[2]) : 0;
+  g_n128 = argc > 3 ? atoi(argv[3]) : 0;
+  printf("operands: %s, MMA N = %d\n", g_random ? "pseudo-random" : "constant", g_n128 ? 128 : 256);
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   long long* d_cycles; unsigned* d_sink;
   cudaMalloc(&d_cycles, sms * sizeof(long long));
   cudaMalloc(&d_sink, 4);
+  for (int m = 8; m <= 10; ++m)
+    printf("mode %d (MMA only + %s): %.0f cycles per tile per SM\n", m,
+           m == 8 ? "a second tcgen05.commit per tile" : m == 9 ? "second commit + stage-barrier wait (producer thread re-arms)"
+                                                                 : "second commit + stage-barrier wait + clock64 reads",
+           run<8>(sms, tiles, m, d_cycles, d_sink));
   const char* names[8] = {"MMA only", "MMA + fp32 read-out", "MMA(f16 acc) + packed 16-bit read-out", "fp32 read-out only",
                           "packed 16-bit read-out only", "MMA + fp32 read-out + max-tree filter, 8 epilogue warps",
                           "MMA + fp32 read-out + max-tree filter, 16 epilogue warps",
