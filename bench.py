@@ -21,6 +21,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -426,6 +427,11 @@ def run_product(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_s, score_ms_mean = t.tolist()
 
+    # per-kernel device times of the step (CUPTI trace, separate untimed pass; every rank runs the same steps --
+    # the multi-GPU step exchanges data -- rank 0 reports)
+    trace = kernel_trace(lambda: step(ids_dev))
+    barrier()
+
     # ---- sub-records: the literal config-3 curve (4096 users IN TOTAL, strong scaling) and a non-zero bias ----
     sub = {}
     last_strong = None
@@ -537,7 +543,6 @@ def run_product(args, rank, world, local_rank):
         "sub_records": sub,
     }
     # ---- secondary kernels: HBM fractions (north_star asks for scan / merge / metrics / verbalizer) ----
-    trace = kernel_trace(lambda: step(ids_dev))
     if trace is not None:
         mine = {k: v for k, v in trace.items() if "lrb::" in k or k.startswith("lrb")}
         line["gpu_launches"] = int(round(sum(c for c, _ in mine.values()) * args.steps))
@@ -546,7 +551,8 @@ def run_product(args, rank, world, local_rank):
         users_step = scored_users
         sec = {}
         for name, (cnt, us) in sorted(mine.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
-            short = name.split("(")[0].split("<")[0].split("::")[-1]
+            mname = re.search(r"(\w+_kernel)", name)
+            short = mname.group(1) if mname else name.split("(")[0].split("<")[0].split("::")[-1]
             rec = {"launches_per_step": cnt, "us_per_launch": us}
             if short == "lru_scan_kernel":
                 # reads bu once, writes h once: 2 KB per token in the first block, 1 KB + 1 KB per user in the last

@@ -29,23 +29,21 @@ __global__ void prepare_table_kernel(const float* __restrict__ table, const floa
     bias_pad[i] = bv;
     if (bias_blk != nullptr) {
       // folded-bias block consumed by the scoring GEMM as a K=16 slab: bias = hi + mid + lo (three
-      // bf16 terms reproduce the fp32 value to ~2^-24), laid out per 256-item tile in the UMMA
-      // no-swizzle K-major canonical form: 8-row groups of 256 B = [K 0..7 core matrix][K 8..15].
+      // bf16 terms reproduce the fp32 value to ~2^-24), stored as a plain row-major [rows_pad][16] bf16
+      // matrix (32 B per item: K columns 0..2 = hi, mid, lo, the rest zero); TMA brings it into shared
+      // memory with the 32-byte swizzle the UMMA descriptor expects.
       const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
       float rest = i < rows ? bv - __bfloat162float(hi) : 0.f;
       const __nv_bfloat16 mid = __float2bfloat16_rn(rest);
       rest = i < rows ? rest - __bfloat162float(mid) : 0.f;
       const __nv_bfloat16 lo = __float2bfloat16_rn(rest);
-      const long long tile = i >> 8;
-      const int r = static_cast<int>(i & 255);
-      const long long grp16 = tile * 512 + (r >> 3) * 16;   // in 16-byte units: 8 KB = 512 units / tile
       uint4 k_lo;
       k_lo.x = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) |
                (static_cast<uint32_t>(__bfloat16_as_ushort(mid)) << 16);
       k_lo.y = static_cast<uint32_t>(__bfloat16_as_ushort(lo));
       k_lo.z = 0u; k_lo.w = 0u;
-      bias_blk[grp16 + (r & 7)] = k_lo;                        // K columns 0..7
-      bias_blk[grp16 + 8 + (r & 7)] = make_uint4(0u, 0u, 0u, 0u);  // K columns 8..15
+      bias_blk[2 * i] = k_lo;                               // K columns 0..7
+      bias_blk[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);     // K columns 8..15
     }
   }
 }

@@ -6,6 +6,9 @@
 #include "api_util.h"
 #include "score_topk_tc.cuh"
 
+#ifndef LRB_CAP_DIV
+#define LRB_CAP_DIV 1   // users per scoring launch = (SM pairs / LRB_CAP_DIV) x 256
+#endif
 #ifndef LRB_NS_PAIR
 #define LRB_NS_PAIR 4   // TMA stages of the K <= 20 CTA-pair kernel (20 KB each)
 #endif
@@ -225,7 +228,11 @@ Decomp decompose(int B, long long rows, int units, int bm = tc::BM) {
 // 8.85 ms, 5632: 8.70, 8192: 8.39, 9472 (+ one of 4352): 8.30, 18944 (no union bound): 10.2.
 inline int users_per_launch(int B, int sms) {
   const int units = sms >= 2 ? sms / 2 : 1;                 // CTA pairs
-  int cap_tiles = units / (g_debug_cap_div > 0 ? g_debug_cap_div : 2);   // pair tiles (256 users) per launch
+  // one pair tile (256 users) per CTA pair: every user has ONE full stream over the whole local item range, so each
+  // streaming top-K restarts once (two slots per user, union bound with c = ceil(K/2) <= 12).  Measured on B200,
+  // 32768 users x 1.25M rows (one rank's call of the 8-GPU data-parallel step): launches of 9472 users (two full
+  // streams, c = 5) 5.58 ms, of 18944 users 5.38 ms.
+  int cap_tiles = units / (g_debug_cap_div > 0 ? g_debug_cap_div : LRB_CAP_DIV);   // pair tiles per launch
   if (cap_tiles < 1) cap_tiles = 1;
   const int cap = cap_tiles * 2 * tc::BM;
   return B <= cap ? B : cap;
@@ -291,17 +298,17 @@ int make_tmap_bf16_k64(CUtensorMap* out, const void* ptr, unsigned long long row
   return LRB_OK;
 }
 
-// folded-bias blocks as a [bytes/256][256] uint8 matrix: a CTA of a pair fetches its 4 KB half as a
-// 16-row box (lands contiguously; no swizzle), accounted on the leader's barrier like the item rows
-int make_tmap_bias_blocks(CUtensorMap* out, const void* ptr, unsigned long long n_tiles) {
+// folded-bias block: row-major [n_tiles * 256][16] bf16 (32 B per item), box = 16 x box_rows (the whole tile, or a CTA
+// pair's 128-row half), 32-byte swizzle
+int make_tmap_bias_blocks(CUtensorMap* out, const void* ptr, unsigned long long n_tiles, unsigned box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(LRB_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {256ull, n_tiles * (tc::BIASBLK_BYTES / 256)};
-  cuuint64_t strides[1] = {256ull};
-  cuuint32_t box[2] = {256u, static_cast<cuuint32_t>(tc::BIASBLK_BYTES / 2 / 256)};
+  cuuint64_t dims[2] = {16ull, n_tiles * tc::BN};
+  cuuint64_t strides[1] = {32ull};
+  cuuint32_t box[2] = {16u, box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(LRB_ERR_DRIVER, "cuTensorMapEncodeTiled (bias blocks) failed (%d)", (int)r);
   return LRB_OK;
@@ -312,11 +319,11 @@ int make_tmap_bias_blocks(CUtensorMap* out, const void* ptr, unsigned long long 
 inline int epilogue_warps_for(int K) { return K <= 20 ? LRB_EW20 : 8; }
 
 // `grid` counts MMA engines: CTAs for CG == 1, CTA pairs (clusters of 2) for CG == 2.
-template <int KMAX, int NS, bool kDense, int CG, int EW, int PROBE = 0>
+template <int KMAX, int NS, bool kDense, int CG, int EW, int PROBE = 0, int CMAX = tc::MAX_C_SHARE_SMALL>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbias, const tc::ScoreParams& p,
               int grid, cudaStream_t st, bool overlap_prev = false) {
   using L = tc::SmemLayout<KMAX, NS, CG, EW>;
-  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG, EW, PROBE>;
+  auto kern = tc::score_topk_tc_kernel<KMAX, NS, kDense, CG, EW, CMAX, PROBE>;
   LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid * CG));
@@ -457,14 +464,18 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
   LRB_REQUIRE(scratch != nullptr, "lrb_score_topk: scratch is required for the bf16 path");
   const int want_slots = chunked_slots(B, rows, sms);
   LRB_REQUIRE(slots == want_slots, "lrb_score_topk: slots=%d but lrb_score_topk_slots says %d", slots, want_slots);
-  CUtensorMap tb1, tb2, tbias;
+  CUtensorMap tb1, tb2, tbias, tbias1;
   rc = make_tmap_bf16_k64(&tb1, table, static_cast<unsigned long long>(rows), tc::BN);
   if (rc != LRB_OK) return rc;
   rc = make_tmap_bf16_k64(&tb2, table, static_cast<unsigned long long>(rows), tc::BN / 2);
   if (rc != LRB_OK) return rc;
-  tbias = tb1;   // placeholder when there is no bias block (never dereferenced)
+  tbias = tb1;   // placeholders when there is no bias block (never dereferenced)
+  tbias1 = tb1;
   if (bias_blk != nullptr) {
-    rc = make_tmap_bias_blocks(&tbias, bias_blk, static_cast<unsigned long long>((rows + tc::BN - 1) / tc::BN));
+    const unsigned long long nt = static_cast<unsigned long long>((rows + tc::BN - 1) / tc::BN);
+    rc = make_tmap_bias_blocks(&tbias, bias_blk, nt, tc::BN / 2);     // a CTA pair's halves
+    if (rc != LRB_OK) return rc;
+    rc = make_tmap_bias_blocks(&tbias1, bias_blk, nt, tc::BN);        // single CTAs: the whole tile
     if (rc != LRB_OK) return rc;
   }
   LRB_CUDA_TRY(cudaMemsetAsync(part_cnt, 0, static_cast<size_t>(B) * slots * sizeof(int), st));
@@ -499,7 +510,9 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
       // entries each of the PARTS*s_full full-stream threads of a user must hold for the union bound
       const int parts = epilogue_warps_for(K) / 4;
       const int c = d.s_full > 0 ? (K + parts * d.s_full - 1) / (parts * d.s_full) : 99;
-      p.c_share = c <= tc::MAX_C_SHARE ? c : 0;
+      // (the K <= 20 CTA-pair kernel also exists with room for c <= 12: one full stream per user)
+      const int c_max = (cg == 2 && K <= 20) ? tc::MAX_C_SHARE_LARGE : tc::MAX_C_SHARE_SMALL;
+      p.c_share = c <= c_max ? c : 0;
       // scout pass: worth its T0 extra tiles when the union bound exists and segments are long enough
       const long long seg_tiles = d.s_full > 0 ? d.full_tiles / d.s_full : 0;
       p.scout_tiles = (p.c_share > 0 && seg_tiles >= 128) ? 16 : 0;
@@ -526,24 +539,26 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
            : m == 5 ? launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 5>(ta, tb2, tbias, p, d.grid, st, ov)
                     : launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 6>(ta, tb2, tbias, p, d.grid, st, ov);
       } else {
-        rc = m == 1 ? launch_tc<20, 2, false, 1, LRB_EW20, 1>(ta, tb1, tbias, p, d.grid, st, ov)
-           : m == 2 ? launch_tc<20, 2, false, 1, LRB_EW20, 2>(ta, tb1, tbias, p, d.grid, st, ov)
-           : m == 4 ? launch_tc<20, 2, false, 1, LRB_EW20, 4>(ta, tb1, tbias, p, d.grid, st, ov)
-           : m == 5 ? launch_tc<20, 2, false, 1, LRB_EW20, 5>(ta, tb1, tbias, p, d.grid, st, ov)
-                    : launch_tc<20, 2, false, 1, LRB_EW20, 6>(ta, tb1, tbias, p, d.grid, st, ov);
+        rc = m == 1 ? launch_tc<20, 2, false, 1, LRB_EW20, 1>(ta, tb1, tbias1, p, d.grid, st, ov)
+           : m == 2 ? launch_tc<20, 2, false, 1, LRB_EW20, 2>(ta, tb1, tbias1, p, d.grid, st, ov)
+           : m == 4 ? launch_tc<20, 2, false, 1, LRB_EW20, 4>(ta, tb1, tbias1, p, d.grid, st, ov)
+           : m == 5 ? launch_tc<20, 2, false, 1, LRB_EW20, 5>(ta, tb1, tbias1, p, d.grid, st, ov)
+                    : launch_tc<20, 2, false, 1, LRB_EW20, 6>(ta, tb1, tbias1, p, d.grid, st, ov);
       }
       if (rc != LRB_OK) return rc;
       continue;
     }
 #endif
     if (cg == 2) {
-      if (K <= 20) rc = launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20>(ta, tb2, tbias, p, d.grid, st, ov);
+      if (K <= 20 && p.c_share > tc::MAX_C_SHARE_SMALL)
+        rc = launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20, 0, tc::MAX_C_SHARE_LARGE>(ta, tb2, tbias, p, d.grid, st, ov);
+      else if (K <= 20) rc = launch_tc<20, LRB_NS_PAIR, false, 2, LRB_EW20>(ta, tb2, tbias, p, d.grid, st, ov);
       else if (K <= 32) rc = launch_tc<32, 4, false, 2, 8>(ta, tb2, tbias, p, d.grid, st, ov);
       else rc = launch_tc<50, 3, false, 2, 8>(ta, tb2, tbias, p, d.grid, st, ov);
     } else {
-      if (K <= 20) rc = launch_tc<20, 2, false, 1, LRB_EW20>(ta, tb1, tbias, p, d.grid, st, ov);
-      else if (K <= 32) rc = launch_tc<32, 3, false, 1, 8>(ta, tb1, tbias, p, d.grid, st, ov);
-      else rc = launch_tc<50, 2, false, 1, 8>(ta, tb1, tbias, p, d.grid, st, ov);
+      if (K <= 20) rc = launch_tc<20, 2, false, 1, LRB_EW20>(ta, tb1, tbias1, p, d.grid, st, ov);
+      else if (K <= 32) rc = launch_tc<32, 3, false, 1, 8>(ta, tb1, tbias1, p, d.grid, st, ov);
+      else rc = launch_tc<50, 2, false, 1, 8>(ta, tb1, tbias1, p, d.grid, st, ov);
     }
     if (rc != LRB_OK) return rc;
   }
@@ -592,7 +607,12 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
   p.gslots = nullptr; p.gstride = 0; p.pair_drain = 0; p.c_share = 0; p.scout_tiles = 0; p.ring = nullptr; p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
   p.dense_out = out; p.dense_ld = ld_out; p.probe_out = nullptr;
   p.s_full = d.s_full; p.rem = d.rem; p.full_tiles = d.full_tiles; p.y_tiles = d.y_tiles;
-  return launch_tc<20, 3, true, 1, 8>(ta, tb, tb, p, d.grid, st);
+  CUtensorMap tbias = tb;   // placeholder without a bias block (never dereferenced)
+  if (bias_blk != nullptr) {
+    rc = make_tmap_bias_blocks(&tbias, bias_blk, static_cast<unsigned long long>((rows + tc::BN - 1) / tc::BN), tc::BN);
+    if (rc != LRB_OK) return rc;
+  }
+  return launch_tc<20, 3, true, 1, 8>(ta, tb, tbias, p, d.grid, st);
 }
 
 }  // extern "C"

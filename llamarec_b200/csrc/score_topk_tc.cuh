@@ -49,9 +49,9 @@ struct ScoreParams {
   int n_tiles;       // ceil(rows / 256)
   int row_offset;    // global item id of local row 0
   int K;             // list length (<= KMAX)
-  const uint8_t* bias_blk;     // folded bias: [n_tiles] tiles of BIASBLK_BYTES (canonical no-swizzle
-                               // K-major [256][16] bf16: col 0..2 = hi/mid/lo split of bias, -inf
-                               // in col 0 beyond `rows`); nullptr = bias is identically zero
+  const uint8_t* bias_blk;     // folded bias: row-major [n_tiles * 256][16] bf16 (col 0..2 = hi/mid/lo split of the
+                               // bias, -inf in col 0 beyond `rows`), fetched through tmap_bias with the 32-byte
+                               // swizzle; nullptr = bias is identically zero
   const int* excl_sorted;      // [B][excl_stride] ascending global ids, INT_MAX padded; null = none
   const uint32_t* excl_bloom;  // [B][4] 128-bit membership filter over (id & 127)
   int excl_stride;
@@ -241,11 +241,11 @@ constexpr int RING_GROUPS = LRB_RING_GROUPS;
 constexpr int RING_REC_BYTES = 80;   // 16 fp32 + int32 gid0, padded to a multiple of 16 B
 
 // c-th largest score of an unsorted set (1 <= c <= MAX_C_SHARE); -inf if the set holds fewer than c entries.
-#ifndef LRB_MAX_C_SHARE
-#define LRB_MAX_C_SHARE 6
-#endif
-constexpr int MAX_C_SHARE = LRB_MAX_C_SHARE;
-template <int STRIDE>
+// MAX_C_SHARE (kernel template parameter CMAX) is 6 for launches whose users have >= 4 full-stream slots and 12 for
+// the large launches of the data-parallel multi-GPU step (one full stream = 2 slots per user, c = 10 at K = 20).
+constexpr int MAX_C_SHARE_SMALL = 6;
+constexpr int MAX_C_SHARE_LARGE = 12;
+template <int STRIDE, int MAX_C_SHARE>
 LRB_DEVINL float set_cth_best(uint32_t ls, uint32_t ln, int c) {
   const int n = lds_s32(ln);
   float m[MAX_C_SHARE];   // running top-MAX_C_SHARE, descending
@@ -344,7 +344,7 @@ struct DrainState {
 
 // Lock-step drain of the warp's rings (compact_ring) + publication of the improved bounds.  Returns the thread's
 // own K-th best.
-template <int STRIDE, int KMAX>
+template <int STRIDE, int KMAX, int CMAX>
 __device__ __noinline__ float drain_rings(DrainState* st, int cnt, float own_thr) {
   float shared_thr = -INFINITY;
   if (st->live) {
@@ -357,7 +357,7 @@ __device__ __noinline__ float drain_rings(DrainState* st, int cnt, float own_thr
   if (st->live) {
     if (own_thr > -INFINITY) atomicMax(st->rowthr, float_to_key(own_thr));   // sibling column half
     if (st->gslot != nullptr) {
-      const float cb = set_cth_best<STRIDE>(st->ls, st->ln, st->c_share);
+      const float cb = set_cth_best<STRIDE, CMAX>(st->ls, st->ln, st->c_share);
       const int key = float_to_key(cb);
       if (cb > -INFINITY && key > st->published) {
         st->published = key;
@@ -401,16 +401,18 @@ struct SmemLayout {
   static_assert(DONE_RING > NS, "the producer looks NS tiles back in the ring of 'tile computed' barriers");
 };
 
-// No-swizzle K-major canonical layout of a [rows][16] bf16 block (UMMA "INTERLEAVE"): 8x8 core
-// matrices of 128 contiguous bytes; the two core matrices of one 8-row group (K halves) are LBO =
-// 128 B apart, consecutive 8-row groups SBO = 256 B apart.
-LRB_DEVINL uint64_t umma_desc_k16_nosw(uint32_t smem_addr) {
+// K-major [rows][16] bf16 block (the folded bias and its "ones" partner): rows are exactly one 32-byte swizzle atom
+// wide, 8-row groups are 256 B apart (SBO), LBO unused; layout type 6 = SWIZZLE_32B (16-byte chunk index XOR bit 2
+// of the row).  The first version used the no-swizzle "interleave" layout, whose K = 16 MMA took ~500 cycles per tile
+// instead of ~130.
+LRB_DEVINL uint64_t umma_desc_k16_sw32(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
-  d |= static_cast<uint64_t>(128 >> 4) << 16;   // LBO
+  d |= static_cast<uint64_t>(1) << 16;          // LBO (ignored)
   d |= static_cast<uint64_t>(256 >> 4) << 32;   // SBO
   d |= static_cast<uint64_t>(1) << 46;          // version
-  return d;                                     // layout type 0 = no swizzle
+  d |= static_cast<uint64_t>(6) << 61;          // SWIZZLE_32B
+  return d;
 }
 
 // PROBE (developer harness only, tools/tc_check; the library instantiates PROBE == 0):
@@ -429,7 +431,7 @@ LRB_DEVINL uint64_t umma_desc_k16_nosw(uint32_t smem_addr) {
 // not `tcgen05.mma` shows up as idle tensor-pipe cycles (measured, tools/tmem_probe modes 8-10: a second commit per
 // tile costs 80-130 cycles, a second barrier wait ~120).  Hence one commit per tile, and the two things it has to
 // wait for (operands landed, accumulator stage drained) are polled by two lanes of the MMA warp in ONE try_wait.
-template <int KMAX, int NS, bool kDense, int CG, int EW, int PROBE = 0>
+template <int KMAX, int NS, bool kDense, int CG, int EW, int CMAX = MAX_C_SHARE_SMALL, int PROBE = 0>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b,
@@ -438,6 +440,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
   constexpr int EPI_THREADS = EW * 32;
+  constexpr int MAX_C_SHARE = CMAX;
   constexpr int PARTS = EW / 4;            // column parts of a tile
   constexpr int COLS = BN / PARTS;         // columns per epilogue thread and tile (128 or 64)
   constexpr int CH = COLS / 32;            // x32 TMEM loads per thread and tile (4 or 2)
@@ -505,10 +508,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 3) {
     // "ones" block: column 0..2 = 1.0 (they multiply the hi/mid/lo bf16 terms of the bias)
     for (int i = lane; i < ONES_BYTES / 2; i += 32) {
-      // canonical no-swizzle layout: element (row, k) at (row/8)*256 + (k/8)*128 + (row%8)*16 + (k%8)*2
-      const int rem = i & 127;
-      const int khalf = rem >> 6;
-      const int k = khalf * 8 + (rem & 7);
+      // 32-byte-swizzled K-major layout: element (row, k) at row*32 + ((k/8) ^ ((row/4)&1))*16 + (k%8)*2
+      const int row = i >> 4;
+      const int chunk = ((i >> 3) & 1) ^ ((row >> 2) & 1);   // logical K half stored in this physical chunk
+      const int k = chunk * 8 + (i & 7);
       reinterpret_cast<__nv_bfloat16*>(sOnes)[i] = __float2bfloat16(k < 3 ? 1.0f : 0.0f);
     }
     // make the generic-proxy writes visible to the tensor core (async proxy)
@@ -561,14 +564,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint32_t full_lead = mapa_u32(smem_u32(&full_bar[stage]), 0);
             tma_load_2d_pair(st, &tmap_b, full_lead, 0, n * BN + static_cast<int>(cta_rank) * (BN / 2));
             if (has_bias)
-              tma_load_2d_pair(st + L::kBBytes, &tmap_bias, full_lead, 0,
-                               n * (BIASBLK_BYTES / 256) + static_cast<int>(cta_rank) * (L::kBiasBytes / 256));
+              tma_load_2d_pair(st + L::kBBytes, &tmap_bias, full_lead, 0, n * BN + static_cast<int>(cta_rank) * (BN / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], stage_tx);
             tma_load_2d(st, &tmap_b, &full_bar[stage], 0, n * BN);
-            if (has_bias)
-              bulk_load_1d(st + B_BYTES, p.bias_blk + static_cast<size_t>(n) * BIASBLK_BYTES,
-                           BIASBLK_BYTES, &full_bar[stage]);
+            if (has_bias) tma_load_2d(st + B_BYTES, &tmap_bias, &full_bar[stage], 0, n * BN);
           }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
@@ -591,7 +591,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int seg_idx = 0;
       int t = 0;
       const uint64_t desc_a0 = umma_desc_k_sw128(smem_u32(sA));
-      const uint64_t desc_ones = umma_desc_k16_nosw(smem_u32(sOnes));
+      const uint64_t desc_ones = umma_desc_k16_sw32(smem_u32(sOnes));
       const uint32_t d_addr = tmem_base + static_cast<uint32_t>(mw * BN);
       long long probe_wait = 0;
       while (walk.next(sg)) {
@@ -624,8 +624,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
               // folded bias: D += ones[128x16] * bias_blk[256x16]^T  (hi + mid + lo bf16 terms)
               if (has_bias) {
-                if (CG == 2) umma_bf16_ss_pair(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
-                else umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_nosw(st + L::kBBytes), idesc, 1u);
+                if (CG == 2) umma_bf16_ss_pair(d_addr, desc_ones, umma_desc_k16_sw32(st + L::kBBytes), idesc, 1u);
+                else umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_sw32(st + L::kBBytes), idesc, 1u);
               }
             }
             // ONE commit: "tile t computed" = accumulator full (epilogues) + shared-memory stage free (producers)
@@ -857,11 +857,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (PROBE != 0) {
           const long long d0 = clock64();
           probe_appends += cnt;
-          own_thr = drain_rings<EPI_THREADS, KMAX>(&dst, cnt, own_thr);
+          own_thr = drain_rings<EPI_THREADS, KMAX, CMAX>(&dst, cnt, own_thr);
           probe_drain_cyc += clock64() - d0;
           probe_drains += 1;
         } else {
-          own_thr = drain_rings<EPI_THREADS, KMAX>(&dst, cnt, own_thr);
+          own_thr = drain_rings<EPI_THREADS, KMAX, CMAX>(&dst, cnt, own_thr);
         }
         cnt = 0;
       };

@@ -50,6 +50,23 @@ for it in range(3):
     d2 = sh.retrieve_dp(ids[sl].cuda(), k=20, labels=labels[sl].cuda(), ks=[1, 5, 10, 20])
     ref2 = ref_model.retrieve(ids[sl].cuda(), k=20, precision="bf16")
     assert torch.equal(d2["ids"], ref2["ids"]) and torch.equal(d2["scores"], ref2["scores"]), f"peer step {it}"
+# one user per rank (2 users in total) over the collective path: the [B, 2, k] payload must not be mistaken for [2, B, k]
+d1 = shc.retrieve_dp(ids[rank:rank + 1].cuda(), k=20, labels=labels[rank:rank + 1].cuda(), ks=[1, 5, 10, 20])
+assert torch.equal(d1["ids"], ref["ids"][rank:rank + 1]) and torch.equal(d1["scores"], ref["scores"][rank:rank + 1]), "b=1"
+d1p = sh.retrieve_dp(ids[rank:rank + 1].cuda(), k=20, labels=labels[rank:rank + 1].cuda(), ks=[1, 5, 10, 20])
+assert torch.equal(d1p["ids"], ref["ids"][rank:rank + 1]), "b=1 peer"
+# more gathered users than one scoring launch takes (2 x 5000 > 9472): consecutive chunk launches (programmatic
+# dependent launch) inside the data-parallel step
+big_ids, big_lab = synth.make_sequences_fast(10000, n_items, 50, seed=9)
+bb = 5000
+mine = slice(rank * bb, (rank + 1) * bb)
+dbig = sh.retrieve_dp(big_ids[mine].cuda(), k=20, labels=big_lab[mine].cuda(), ks=[1, 5, 10, 20])
+rbig = ref_model.retrieve(big_ids[mine].cuda(), k=20, labels=big_lab[mine].cuda(), ks=[1, 5, 10, 20], precision="bf16")
+assert torch.equal(dbig["ids"], rbig["ids"]) and torch.equal(dbig["scores"], rbig["scores"]), "chunked dp"
+assert torch.equal(dbig["label_rank"], rbig["label_rank"])
+# 'auto' precision is resolved from the whole catalogue, identically on every rank
+auto = CudaBackend(m, rank, world, precision="auto")
+assert auto.precision == "bf16"
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
