@@ -6,6 +6,9 @@
 #include "api_util.h"
 #include "score_topk_tc.cuh"
 
+#ifndef LRB_RESTART_TILES
+#define LRB_RESTART_TILES 150.0   // cost of one streaming top-K (re)start, in item tiles (see decompose())
+#endif
 #ifndef LRB_CAP_DIV
 #define LRB_CAP_DIV 1   // users per scoring launch = (SM pairs / LRB_CAP_DIV) x 256
 #endif
@@ -21,9 +24,12 @@
 // Developer-harness knobs (tools/tc_check is built with -DLRB_DEBUG_MODES; the library never is).
 #ifdef LRB_DEBUG_MODES
 static int g_debug_cap_div = 0;
+static double g_debug_restart_tiles = -1.0;
 extern "C" void lrb_debug_set_cap_div(int v) { g_debug_cap_div = v; }
+extern "C" void lrb_debug_set_restart_tiles(double v) { g_debug_restart_tiles = v; }
 #else
 static const int g_debug_cap_div = 0;
+static const double g_debug_restart_tiles = -1.0;
 #endif
 
 namespace lrb {
@@ -206,9 +212,18 @@ Decomp decompose(int B, long long rows, int units, int bm = tc::BM) {
     d.y_tiles = 0;
     d.full_tiles = d.n_tiles;
   } else {
-    // per-CTA work: full stream = full_tiles / s_full ; shared stream = m_tiles * y / rem
-    double y = static_cast<double>(d.n_tiles) /
-               (static_cast<double>(d.s_full) * d.m_tiles / d.rem + 1.0);
+    // per-CTA work in item tiles: full stream = full_tiles / s_full ; shared stream = m_tiles * y / rem -- plus what
+    // every (re)start of a streaming top-K costs (thresholds are weak at first: candidate appends and drains; measured
+    // ~0.45M cycles for a full-stream segment; shared-stream segments start under the full streams' union bound and
+    // are cheaper -- A/B on one B200: R0 = 0 / 150 / 300 / 600 tiles give 4.97 / 4.84 / 4.93 / 4.91 ms at 4096 x 10M
+    // and 5.44 / 5.40 / 5.52 / 5.58 ms at 32768 x 1.25M, hence R0 = 150).  A full-stream CTA starts once, a
+    // shared-stream CTA about m_tiles / rem + 1/2 times:
+    //   (n - y) / s + R0  =  m * y / rem + (m / rem + 1/2) * R0
+    double R0 = g_debug_restart_tiles >= 0 ? g_debug_restart_tiles : LRB_RESTART_TILES;
+    if (R0 > d.n_tiles / (8.0 * d.s_full)) R0 = d.n_tiles / (8.0 * d.s_full);   // short segments: a start costs less
+    const double m_over_rem = static_cast<double>(d.m_tiles) / d.rem;
+    double y = (static_cast<double>(d.n_tiles) / d.s_full + R0 * (0.5 - m_over_rem)) / (1.0 / d.s_full + m_over_rem);
+    if (y < 0.0) y = 0.0;
     d.y_tiles = static_cast<int>(std::floor(y + 0.5));
     if (d.y_tiles > d.n_tiles) d.y_tiles = d.n_tiles;
     if (d.y_tiles <= 0) { d.y_tiles = 0; d.rem = 0; }

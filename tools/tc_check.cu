@@ -37,6 +37,7 @@ extern "C" void lrb_debug_set_probe_out(long long* p);
 extern "C" void lrb_debug_set_pair_drain(int v);
 extern "C" void lrb_debug_set_overlap(int v);
 extern "C" void lrb_debug_set_cap_div(int v);
+extern "C" void lrb_debug_set_restart_tiles(double v);
 
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
@@ -359,6 +360,7 @@ int main(int argc, char** argv) {
     lrb_debug_set_score_mode(mode);
     if (mode) printf("debug mode %d\n", mode);
     const int which = argc > 10 ? atoi(argv[10]) : 3;   // bit 0: with bias + exclusion, bit 1: without
+    if (argc > 11) { lrb_debug_set_restart_tiles(atof(argv[11])); printf("restart cost %s tiles\n", argv[11]); }
     if (which & 1) time_topk(B, rows, K, true, true);
     if (which & 2) time_topk(B, rows, K, false, false);
     return 0;
