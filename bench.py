@@ -429,13 +429,18 @@ def run_product(args, rank, world, local_rank):
 
     # per-kernel device times of the step (CUPTI trace, separate untimed pass; every rank runs the same steps --
     # the multi-GPU step exchanges data -- rank 0 reports)
-    trace = kernel_trace(lambda: step(ids_dev))
+    trace = None if args.lean else kernel_trace(lambda: step(ids_dev))
     barrier()
 
     # ---- sub-records: the literal config-3 curve (4096 users IN TOTAL, strong scaling) and a non-zero bias ----
     sub = {}
     last_strong = None
     ids_strong = ids_dev
+    if args.lean:
+        if rank == 0:
+            print(json.dumps({"lean": True, "value": (BATCH * world if weak else BATCH) * args.steps / (ms_total * 1e-3),
+                              "ms_per_step": ms_total / args.steps, "kernel_ms": score_ms_mean}), flush=True)
+        return
     if weak:
         ids_strong = make_inputs(42)[0].to(device)                  # the same 4096 users on every rank
         labels_strong = make_inputs(42)[1].to(device)
@@ -628,6 +633,9 @@ def main():
                     help="N > 1, weak scaling: stores into peer memory (default when available) or NCCL collectives")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 4096 users per GPU (default), strong = 4096 users in total")
+    ap.add_argument("--lean", action="store_true",
+                    help="profiling convenience (ncu): only the timed loops -- no kernel trace, sub-records, parity "
+                         "checks or CPU legs")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling convenience: omit the ~20 s CPU oracle leg (the default run includes it)")
     args = ap.parse_args()

@@ -151,6 +151,29 @@ int lrb_ce_loss_fwd(const float* hidden, const float* table_f32, const float* bi
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Train step: loss AND the gradient of every parameter, without the logits tensor.
+ * Replaces LRUTrainer.calculate_loss + loss.backward() (trainer/lru.py:22-28, trainer/base.py:107-111),
+ * i.e. the backward of model/lru.py:38-41,57-60,73-86,149-161,173-175 under
+ * nn.CrossEntropyLoss(ignore_index) (trainer/lru.py:20).  Dropout is the identity; rows must be
+ * left-padded (dataloader/lru.py:98-118) -- otherwise LRB_ERR_UNSUPPORTED.
+ *   ids [B][L] int64/int32 (id_bytes 8/4), labels [B*L] int64
+ *   table_f32 [table_rows][64], bias_f32 [table_rows], weights = the packed blob of lrb_encode_fwd,
+ *   params_log [n_blocks][3][128] (nu_log, theta_log, gamma_log of every block, model/lru.py:119)
+ * Outputs (overwritten)
+ *   loss_sum [2]      sum of the row losses, number of counted rows (loss = [0] / [1])
+ *   grad_weights      lrb_encoder_weight_floats(n_blocks) floats, laid out like `weights`; the
+ *                     lambda_re / lambda_im / gamma slots hold d nu_log / d theta_log / d gamma_log
+ *   grad_table [table_rows][64]  (scoring matmul + embedding gather: the table is tied)
+ *   grad_bias  [table_rows]
+ * Workspace: lrb_train_workspace_bytes(B, L, n_blocks).  Synchronises the stream once (error flag).
+ * ------------------------------------------------------------------------------------------ */
+size_t lrb_train_workspace_bytes(int B, int L, int n_blocks);
+int lrb_train_step(const void* ids, int id_bytes, const int64_t* labels, int B, int L, const float* table_f32,
+                   int64_t table_rows, const float* bias_f32, const float* weights, const float* params_log,
+                   int n_blocks, int64_t ignore_index, float* loss_sum, float* grad_weights, float* grad_table,
+                   float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * k-way merge + Recall/MRR/NDCG + candidate emission, one fused kernel.
  * Replaces absolute_recall_mrr_ndcg_for_ks (trainer/utils.py:43-90), the label membership test and
  * candidate list of LRUTrainer.generate_candidates (trainer/lru.py:82-88, 114-132).

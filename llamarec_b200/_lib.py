@@ -40,6 +40,9 @@ SIGNATURES = {
     "lrb_ce_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "lrb_ce_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
+    "lrb_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lrb_train_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lrb_peer_push": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "lrb_merge_metrics_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
                                           c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),

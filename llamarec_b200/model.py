@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .packing import pack_encoder_weights
+from .packing import pack_encoder_weights, unpack_encoder_grads
 
 SMALL_CATALOGUE_ROWS = 1 << 17   # up to here 'auto' precision scores in exact fp32
 
@@ -38,6 +38,24 @@ def _on_model_device(fn):
         with torch.cuda.device(w.device):
             return fn(self, *args, **kwargs)
     return wrap
+
+
+class _TrainStep(torch.autograd.Function):
+    """loss = CrossEntropyLoss(ignore_index)(model(x).view(-1, N+1), labels.view(-1)) with a backward: ONE call of
+    lrb_train_step computes the loss and the gradient of every parameter (forward activations never leave the
+    library's workspace); backward() hands the stored gradients to autograd, scaled by the incoming gradient.
+    Inputs after (model, x, labels, ignore_index) are the model's parameters in named_parameters() order."""
+
+    @staticmethod
+    def forward(ctx, model, x, labels, ignore_index, *params):
+        loss, grads = model._train_step(x, labels, ignore_index)
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out = tuple(None if g is None else g * grad_out for g in ctx.grads)
+        return (None, None, None, None) + out
 
 
 class _Container(nn.Module):
@@ -220,13 +238,19 @@ class LRURec(nn.Module):
         return out
 
     @_on_model_device
-    @torch.no_grad()
     def ce_loss(self, x: torch.Tensor, labels: torch.Tensor, ignore_index: int = 0,
                 return_row_loss: bool = False):
-        """Value of the train-step loss, `CrossEntropyLoss(ignore_index=0)(model(x).view(-1, N+1), labels.view(-1))`
-        (trainer/lru.py:20-28), without the [B*L, N+1] logits: encoder at every position -> online log-sum-exp
-        over the catalogue fused with the scoring contraction (lrb_ce_loss_fwd, exact fp32).  Forward value
-        only (the kernels have no backward yet); the encoder runs in eval mode (dropout is identity)."""
+        """The train-step loss, `CrossEntropyLoss(ignore_index=0)(model(x).view(-1, N+1), labels.view(-1))`
+        (trainer/lru.py:20-28), without the [B*L, N+1] logits.  With autograd enabled (and no per-row losses asked
+        for) the result carries a backward: `loss.backward()` fills `.grad` of every parameter from ONE fused
+        forward + backward pass (lrb_train_step), like trainer/base.py:107-111 does through torch's autograd.
+        Under torch.no_grad() it is the forward value only (lrb_ce_loss_fwd).  Dropout is the identity in both."""
+        if torch.is_grad_enabled() and not return_row_loss and any(p.requires_grad for p in self.parameters()):
+            return _TrainStep.apply(self, x, labels, int(ignore_index), *[p for _, p in self.named_parameters()])
+        with torch.no_grad():
+            return self._ce_loss_value(x, labels, ignore_index, return_row_loss)
+
+    def _ce_loss_value(self, x, labels, ignore_index, return_row_loss):
         lib = _lib.load()
         if self.row_begin != 0 or self.row_end != self.num_items + 1:
             raise RuntimeError("ce_loss needs the whole item table on this device (no row shard)")
@@ -247,6 +271,48 @@ class LRURec(nn.Module):
                                        _lib.ptr(ws), ws_bytes, _lib.stream_handle()))
         loss = acc[0] / acc[1]                                       # nan when every label is ignored, like torch
         return (loss, row_loss.view(B, L)) if return_row_loss else loss
+
+    @torch.no_grad()
+    def _train_step(self, x: torch.Tensor, labels: torch.Tensor, ignore_index: int = 0):
+        """-> (loss, [gradient per parameter in named_parameters() order]) from one lrb_train_step call."""
+        lib = _lib.load()
+        if self.row_begin != 0 or self.row_end != self.num_items + 1:
+            raise RuntimeError("the train step needs the whole item table on this device (no row shard)")
+        c = self._prepare()
+        dev = c["table_f32"].device
+        x = x.to(dev).contiguous()
+        if x.dtype not in (torch.int64, torch.int32):
+            x = x.to(torch.int64)
+        B, L = x.shape
+        rows = self.num_items + 1
+        labels = labels.to(dev).reshape(-1).to(torch.int64).contiguous()
+        if labels.numel() != B * L:
+            raise ValueError(f"labels has {labels.numel()} entries, expected B*L = {B * L}")
+        n_blocks = c["n_blocks"]
+        params_log = torch.stack([blk.lru_layer.params_log.detach().float() for blk in self.model.lru_blocks]).contiguous()
+        bias = self.model.bias.detach().float().contiguous()
+        ws_bytes = lib.lrb_train_workspace_bytes(B, L, n_blocks)
+        ws = self._buf(("train_ws", B, L), (ws_bytes,), torch.uint8, dev)
+        g_w = torch.empty(c["blob"].numel(), dtype=torch.float32, device=dev)
+        g_table = torch.empty(rows, 64, dtype=torch.float32, device=dev)
+        g_bias = torch.empty(rows, dtype=torch.float32, device=dev)
+        acc = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.check(lib.lrb_train_step(_lib.ptr(x), x.element_size(), _lib.ptr(labels), B, L, _lib.ptr(c["table_f32"]), rows,
+                                      _lib.ptr(bias), _lib.ptr(c["blob"]), _lib.ptr(params_log), n_blocks,
+                                      int(ignore_index), _lib.ptr(acc), _lib.ptr(g_w), _lib.ptr(g_table), _lib.ptr(g_bias),
+                                      _lib.ptr(ws), ws_bytes, _lib.stream_handle()))
+        loss = acc[0] / acc[1]
+        named = unpack_encoder_grads(g_w, n_blocks)
+        named["embedding.token.weight"] = g_table
+        named["model.bias"] = g_bias
+        grads = []
+        for name, p in self.named_parameters():
+            g = named.get(name)
+            if g is None or not p.requires_grad:
+                grads.append(None)
+            else:
+                grads.append(g.to(p.dtype).reshape(p.shape))
+        return loss, grads
 
     # ------------------------------------------------------------------ internals
     @staticmethod

@@ -56,3 +56,40 @@ def pack_encoder_weights(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     blob = torch.cat([x.reshape(-1).float() for x in parts]).contiguous()
     assert blob.numel() == OFF_BLOCKS + nb * BLOCK_FLOATS, (blob.numel(), nb)
     return blob
+
+
+def unpack_encoder_grads(blob: torch.Tensor, n_blocks: int) -> Dict[str, torch.Tensor]:
+    """Inverse of pack_encoder_weights for the GRADIENT blob lrb_train_step writes (same layout; the lambda_re /
+    lambda_im / gamma slots hold d nu_log / d theta_log / d gamma_log).  Returns tensors keyed by the reference's
+    parameter names, complex where the parameter is complex (real part = dL/dRe, imaginary part = dL/dIm)."""
+    g: Dict[str, torch.Tensor] = {}
+    g["embedding.layer_norm.weight"] = blob[0:D]
+    g["embedding.layer_norm.bias"] = blob[D:2 * D]
+    for i in range(n_blocks):
+        p = f"model.lru_blocks.{i}."
+        o = OFF_BLOCKS + i * BLOCK_FLOATS
+        cur = [o]
+
+        def nxt(n):
+            v = blob[cur[0]:cur[0] + n]
+            cur[0] += n
+            return v
+        g[p + "lru_layer.params_log"] = nxt(3 * H).reshape(3, H)
+        win_t = nxt(D * 2 * H).reshape(D, 2 * H)                  # [64][256], column 2c = Re W_in[c,:], 2c+1 = Im
+        g[p + "lru_layer.in_proj.weight"] = torch.complex(win_t[:, 0::2].t().contiguous(), win_t[:, 1::2].t().contiguous())
+        b_in = nxt(2 * H)
+        g[p + "lru_layer.in_proj.bias"] = torch.complex(b_in[0::2].contiguous(), b_in[1::2].contiguous())
+        wout_t = nxt(2 * H * D).reshape(2 * H, D)                 # row 2c = Re W_out[:,c], row 2c+1 = -Im W_out[:,c]
+        g[p + "lru_layer.out_proj.weight"] = torch.complex(wout_t[0::2].t().contiguous(), (-wout_t[1::2]).t().contiguous())
+        b_out = nxt(D)
+        g[p + "lru_layer.out_proj.bias"] = torch.complex(b_out.contiguous(), torch.zeros_like(b_out))   # Im b_out is unused
+        g[p + "lru_layer.layer_norm.weight"] = nxt(D)
+        g[p + "lru_layer.layer_norm.bias"] = nxt(D)
+        g[p + "feed_forward.w_1.weight"] = nxt(D * FF).reshape(D, FF).t().contiguous()
+        g[p + "feed_forward.w_1.bias"] = nxt(FF)
+        g[p + "feed_forward.w_2.weight"] = nxt(FF * D).reshape(FF, D).t().contiguous()
+        g[p + "feed_forward.w_2.bias"] = nxt(D)
+        g[p + "feed_forward.layer_norm.weight"] = nxt(D)
+        g[p + "feed_forward.layer_norm.bias"] = nxt(D)
+        assert cur[0] == o + BLOCK_FLOATS
+    return g

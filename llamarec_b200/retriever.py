@@ -31,7 +31,8 @@ class LRURetriever:
 
     # ---- trainer/lru.py:22-28 -------------------------------------------------------------------
     def calculate_loss(self, batch) -> torch.Tensor:
-        """Value of the training loss of one batch (forward only; see LRURec.ce_loss)."""
+        """Training loss of one batch; with autograd enabled `loss.backward()` fills the parameters' gradients
+        (fused forward + backward train step, see LRURec.ce_loss)."""
         seqs, labels = batch
         return self.model.ce_loss(seqs, labels)
 

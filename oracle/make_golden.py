@@ -336,6 +336,40 @@ def make_c1_fixture():
           "retrieval_size", out["retrieved"]["test_retrieval"]["retrieval_size"])
 
 
+def make_grad_fixture():
+    """Gradient of the train-step loss w.r.t. EVERY parameter, from the REFERENCE's own autograd
+    (trainer/lru.py:20-28 + loss.backward(), trainer/base.py:107-111) on the committed weights, eval mode (dropout
+    off: the RNG cannot be parity-matched), left-padded batches: `python oracle/make_golden.py grad` writes
+    tests/golden/grad_case.npz."""
+    config, RefLRURec, tutils, tlru, verb = import_reference()
+    N = 400
+    args = SimpleNamespace(num_items=N, bert_hidden_units=64, bert_num_blocks=2, bert_dropout=0.2,
+                           bert_attn_dropout=0.2)
+    d = np.load(os.path.join(OUT, "lru_weights_n400.npz"))
+    sd = {k: torch.from_numpy(d[k]) for k in d.files}
+    out = {}
+    g = torch.Generator().manual_seed(2)
+    for name in ("left_l50", "left_l20"):
+        ref = RefLRURec(args)
+        ref.load_state_dict(sd)
+        ref.eval()
+        fake = SimpleNamespace(model=ref, ce=torch.nn.CrossEntropyLoss(ignore_index=0))
+        ids = torch.from_numpy(np.load(os.path.join(OUT, f"lru_case_{name}.npz"))["ids"])
+        labels = torch.zeros_like(ids)
+        labels[:, :-1] = ids[:, 1:]
+        labels[:, -1] = torch.randint(1, N + 1, (ids.shape[0],), generator=g)
+        labels[ids == 0] = 0
+        loss = tlru.LRUTrainer.calculate_loss(fake, (ids, labels))
+        loss.backward()
+        out[f"{name}_labels"] = labels.numpy()
+        out[f"{name}_loss"] = np.array(loss.item(), dtype=np.float64)
+        for k, p_ in ref.named_parameters():
+            gr = p_.grad
+            out[f"{name}:{k}"] = gr.detach().numpy()
+        print("grad", name, loss.item(), {k: float(p_.grad.abs().max()) for k, p_ in list(ref.named_parameters())[:3]})
+    np.savez_compressed(os.path.join(OUT, "grad_case.npz"), **out)
+
+
 def make_evalset_fixture():
     """LRUValidDataset / LRUTestDataset of the REFERENCE (dataloader/lru.py:129-180) on random user histories:
     `python oracle/make_golden.py evalset` writes tests/golden/evalset_case.npz."""
@@ -372,6 +406,8 @@ if __name__ == "__main__":
         make_verbalizer_handler_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "ce":
         make_ce_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "grad":
+        make_grad_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "c1":
         make_c1_fixture()
     else:

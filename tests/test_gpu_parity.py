@@ -211,9 +211,55 @@ def test_train_step_loss_matches_reference_cross_entropy(model, golden_sd, name)
     loss, rows = model.ce_loss(ids.cuda(), labels.cuda(), return_row_loss=True)
     assert abs(loss.item() - ref) <= 1e-5 * max(1.0, abs(ref)), (loss.item(), ref)
     np.testing.assert_allclose(rows.cpu().numpy(), ce[f"{name}_row_loss"], atol=2e-5, rtol=1e-5)
-    # the retriever-level mirror of LRUTrainer.calculate_loss
+    # the retriever-level mirror of LRUTrainer.calculate_loss (value only here: rows with zeros in the middle have no
+    # backward -- the train step takes the left-padded batches the reference's dataloader produces)
     retr = LRURetriever(_args(400), model)
-    assert abs(retr.calculate_loss((ids.cuda(), labels.cuda())).item() - ref) <= 1e-5 * max(1.0, abs(ref))
+    with torch.no_grad():
+        assert abs(retr.calculate_loss((ids.cuda(), labels.cuda())).item() - ref) <= 1e-5 * max(1.0, abs(ref))
+
+
+@pytest.mark.parametrize("name", ["left_l50", "left_l20"])
+def test_train_step_gradients_match_reference_autograd(golden_sd, name):
+    """loss.backward() through the fused train step (lrb_train_step) against the gradients torch's autograd computes
+    for the REFERENCE model on the same batch (fixture grad_case.npz, `python oracle/make_golden.py grad`):
+    every parameter, rtol 1e-3 (atol = 1e-3 of the gradient's largest entry; fp32 summation order differs)."""
+    gcase = np.load(os.path.join(GOLDEN, "grad_case.npz"))
+    m = LRURec(_args(400))
+    m.load_state_dict(golden_sd)
+    m = m.cuda().train()                                     # dropout is the identity in the kernels either way
+    ids = torch.from_numpy(load_case(name)["ids"]).cuda()
+    labels = torch.from_numpy(gcase[f"{name}_labels"]).cuda()
+    loss = m.ce_loss(ids, labels)
+    assert loss.requires_grad
+    ref_loss = float(gcase[f"{name}_loss"])
+    assert abs(loss.item() - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss)), (loss.item(), ref_loss)
+    (2.0 * loss).backward()                                  # the incoming gradient scales every parameter gradient
+    checked = 0
+    for k, p in m.named_parameters():
+        want = gcase[f"{name}:{k}"]
+        assert p.grad is not None, k
+        got = (p.grad / 2.0).detach().cpu().numpy()
+        assert got.shape == want.shape and got.dtype == want.dtype, (k, got.shape, got.dtype, want.dtype)
+        scale = float(np.abs(want).max())
+        np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-3 * scale + 1e-9, err_msg=k)
+        checked += 1
+    assert checked == len(list(m.named_parameters())) == 30
+    # gradients accumulate like autograd's: a second backward doubles them
+    g0 = m.model.bias.grad.clone()
+    m.ce_loss(ids, labels).backward()
+    assert torch.allclose(m.model.bias.grad, g0 * 1.5, rtol=1e-5, atol=1e-9)
+    # under no_grad the same entry point is the forward value only
+    with torch.no_grad():
+        v = m.ce_loss(ids, labels)
+    assert not v.requires_grad and abs(v.item() - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+
+
+def test_train_step_rejects_rows_that_are_not_left_padded(model):
+    from llamarec_b200._lib import LrbError
+    ids = torch.tensor([[0, 5, 0, 7, 9]], dtype=torch.int64).cuda()
+    labels = torch.tensor([[0, 0, 0, 9, 3]], dtype=torch.int64).cuda()
+    with pytest.raises(LrbError):
+        model.ce_loss(ids, labels)
 
 
 def test_train_step_loss_all_labels_ignored_is_nan(model):

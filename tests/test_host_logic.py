@@ -293,3 +293,23 @@ def test_device_eval_set_matches_reference_datasets():
         assert ds.id_bytes()["int32_device"] * 2 == ds.id_bytes()["int64_reference"]
     sub = DeviceEvalSet(dicts["train"], dicts["test"], L, 8, u2val=dicts["val"], device="cpu", subset_users=test.users[:5])
     assert torch.equal(sub.seqs, test.seqs[:5])
+
+
+def test_gradient_blob_unpack_is_the_inverse_of_weight_packing():
+    """lrb_train_step writes gradients in the layout of the packed weight blob; unpack_encoder_grads must map every slot
+    back to the reference's parameter it was packed from (complex parameters as re + i*im)."""
+    from llamarec_b200 import synth
+    from llamarec_b200.packing import pack_encoder_weights, unpack_encoder_grads
+    sd = synth.make_state_dict(50, seed=1)
+    g = unpack_encoder_grads(pack_encoder_weights(sd), 2)
+    assert len(g) == 2 + 2 * 13
+    for k, v in g.items():
+        if "params_log" in k:                    # those slots carry lambda / gamma, not params_log
+            assert tuple(v.shape) == (3, 128)
+            continue
+        ref = sd[k]
+        assert v.shape == ref.shape and v.dtype == ref.dtype, k
+        if k.endswith("out_proj.bias"):
+            assert torch.equal(v.real, ref.real) and not v.imag.any(), k      # Im b_out never reaches the output
+        else:
+            assert torch.equal(v, ref), k
