@@ -40,7 +40,10 @@ constexpr int DONE_RING = 8;                // "tile computed" barriers (see the
 #ifndef LRB_EW20
 #define LRB_EW20 8
 #endif
-constexpr int SLOT_PARTS = LRB_EW20 / 4;    // partial-list / union-bound slots reserved per stream (>= column parts)
+constexpr int SLOT_PARTS = LRB_EW20 / 4;
+// harness timeline (PROBE builds): clock stamps of CTA 0 for tiles [TL_T0, TL_T0 + TL_N), 24 slots per tile behind the
+// per-CTA counters: {MMA warp woke up, MMA warp committed, 8 x epilogue warp saw "done", 8 x epilogue warp released}
+constexpr int TL_T0 = 2000, TL_N = 16, TL_BASE = 148 * 8;    // partial-list / union-bound slots reserved per stream (>= column parts)
 
 struct ScoreParams {
   int B;             // real users (rows >= B of the padded user matrix are ignored)
@@ -607,9 +610,13 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
               uint64_t* bar = lane == 0 ? &full_bar[stage] : &tmem_empty_bar[mw];
               const uint32_t par = lane == 0 ? static_cast<uint32_t>((t / NS) & 1) : static_cast<uint32_t>(((t >> 1) & 1) ^ 1);
               mbar_wait(bar, par);
+              if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+                p.probe_out[TL_BASE + (t - TL_T0) * 24 + 18 + lane] = clock64();   // operands landed / stage drained
             }
             __syncwarp();
             if (PROBE != 0) probe_wait += clock64() - w0;
+            if (PROBE != 0 && blockIdx.x == 0 && lane == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+              p.probe_out[TL_BASE + (t - TL_T0) * 24 + 0] = clock64();
           }
           if (lane == 0) {
             tc_fence_after();
@@ -631,6 +638,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // ONE commit: "tile t computed" = accumulator full (epilogues) + shared-memory stage free (producers)
             if (CG == 2) umma_commit_pair(&done_bar[t % DONE_RING], 0b11);
             else umma_commit(&done_bar[t % DONE_RING]);
+            if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+              p.probe_out[TL_BASE + (t - TL_T0) * 24 + 1] = clock64();
           }
           __syncwarp();
         }
@@ -699,6 +708,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const long long w0 = clock64();
         mbar_wait(&done_bar[t % DONE_RING], (t / DONE_RING) & 1);
         probe_epi_wait += clock64() - w0;
+        if (blockIdx.x == 0 && lane == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+          p.probe_out[TL_BASE + (t - TL_T0) * 24 + 2 + ew] = clock64();
       } else {
         mbar_wait(&done_bar[t % DONE_RING], (t / DONE_RING) & 1);
       }
@@ -710,6 +721,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (lane == 0) {            // (consecutive mbarriers are 8 bytes apart, in either address window)
         if (CG == 2) mbar_arrive_cluster(acc_empty_addr0 + static_cast<uint32_t>(t % ACC_STAGES) * 8u);
         else mbar_arrive(&tmem_empty_bar[t % ACC_STAGES]);
+        if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+          p.probe_out[TL_BASE + (t - TL_T0) * 24 + 10 + ew] = clock64();
       }
     };
     while (walk.next(sg)) {

@@ -315,14 +315,14 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
     int sms = 0, cc = 0;
     lrb_device_info(&sms, &cc);
     long long* dprobe;
-    CK(cudaMalloc(&dprobe, sms * 8 * sizeof(long long)));
-    CK(cudaMemset(dprobe, 0, sms * 8 * sizeof(long long)));
+    CK(cudaMalloc(&dprobe, (sms * 8 + 16 * 24) * sizeof(long long)));
+    CK(cudaMemset(dprobe, 0, (sms * 8 + 16 * 24) * sizeof(long long)));
     lrb_debug_set_probe_out(dprobe);
     LK(lrb_score_topk(du, T.e16, T.bias_pad, bblk, B, rows, 0, with_excl ? dex : nullptr, with_excl ? dbl : nullptr,
                       stride, K, 0, dps, dpi, dpc, slots, scratch, nullptr));
     CK(cudaDeviceSynchronize());
     lrb_debug_set_probe_out(nullptr);
-    std::vector<long long> st(sms * 8);
+    std::vector<long long> st(sms * 8 + 16 * 24);
     CK(cudaMemcpy(st.data(), dprobe, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     double cyc = 0, ns = 0, ew = 0, me = 0, dc = 0, dn = 0, ap = 0; int n = 0, nl = 0;
     for (int c = 0; c < sms; ++c) if (st[c * 8] > 0) {
@@ -334,6 +334,19 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
              "%.1f drains taking %.3f Mcycles, thread 0 appended %.1f records | MMA warp 1 waited %.3f Mcycles for operands / "
              "a free accumulator stage\n",
              cyc / n / 1e6, ns / n / 1e6, cyc / ns * 1e3, ew / n / 1e6, dn / n, dc / n / 1e6, ap / n, nl ? me / nl / 1e6 : 0.0);
+    if (getenv("LRB_TIMELINE") && st[sms * 8] > 0) {
+      const long long* tl = st.data() + sms * 8;
+      const long long base = tl[0];
+      printf("  timeline of CTA 0 (cycles since the MMA warp woke up for tile T0): per tile  mma_wake mma_commit | done seen by epilogue warps 0-7 | released by warps 0-7\n");
+      for (int i = 0; i < 16; ++i) {
+        printf("   t+%2d %6lld %6lld (ops %6lld stage %6lld) |", i, tl[i * 24] - base, tl[i * 24 + 1] - base, tl[i * 24 + 18] - base,
+               tl[i * 24 + 19] - base);
+        for (int w = 0; w < 8; ++w) printf(" %6lld", tl[i * 24 + 2 + w] - base);
+        printf(" |");
+        for (int w = 0; w < 8; ++w) printf(" %6lld", tl[i * 24 + 10 + w] - base);
+        printf("\n");
+      }
+    }
     cudaFree(dprobe);
   }
   double tflops = 2.0 * B * (double)rows * 64 / (ms * 1e-3) / 1e12;
