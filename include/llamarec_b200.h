@@ -229,19 +229,24 @@ int lrb_merge_metrics_scatter(const float* list_scores, const int32_t* list_ids,
  *        1 = log(softmax over all C*W label words + 1e-15)   (post_log_softmax=True)
  *   round_bf16 != 0: round each logit to bf16 first, as a bf16 lm_head GEMM followed by
  *                    .float() does (model/llm.py:113-114)
+ *   calib_logits: NULL, or [V] fp32 = ManualVerbalizer._calibrate_logits (register_calibrate_logits,
+ *                 trainer/verb.py:202-208): in mode 1 the label-word probabilities are divided by the
+ *                 calibration vector's own label-word probabilities (+1e-15) and renormalised over all
+ *                 label words before the log (ManualVerbalizer.calibrate, trainer/verb.py:616-643)
  *   out [B][C] fp32 : masked mean over the W words of each class (trainer/verb.py:611-614)
  * ------------------------------------------------------------------------------------------ */
 int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head_bf16, int B, int H, int64_t V,
                          const int32_t* word_ids, const uint8_t* word_mask, int C, int W, int mode,
-                         int round_bf16, float* out, void* stream);
+                         int round_bf16, const float* calib_logits, float* out, void* stream);
 
 /* ManualVerbalizer.process_logits on logits that already exist (trainer/verb.py:546-586, the call of
  * trainer/llm.py:68 and demo/inference.py:68): logits [B][ld] fp32 (ld >= V), tok_ids/tok_mask
  * [C][W][T] (sub-tokens of every label word), word_mask [C][W]; handler = handle_multi_token
- * (trainer/verb.py:280-305): 0 first, 1 max, 2 mean; mode as above.  out [B][C]. */
+ * (trainer/verb.py:280-305): 0 first, 1 max, 2 mean; mode and calib_logits as above (the calibration vector goes
+ * through the same handler).  out [B][C]. */
 int lrb_verbalizer_from_logits(const float* logits, int64_t ld, int B, int64_t V, const int32_t* tok_ids,
                                const uint8_t* tok_mask, const uint8_t* word_mask, int C, int W, int T,
-                               int handler, int mode, float* out, void* stream);
+                               int handler, int mode, const float* calib_logits, float* out, void* stream);
 
 #ifdef __cplusplus
 }

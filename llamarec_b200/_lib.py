@@ -47,9 +47,9 @@ SIGNATURES = {
     "lrb_merge_metrics_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
                                           c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "lrb_verbalizer_from_logits": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                           c_int, c_int, c_int, c_void_p, c_void_p]),
+                                           c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "lrb_verbalizer_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_int, c_int,
-                                     c_int, c_int, c_void_p, c_void_p]),
+                                     c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -40,6 +40,9 @@ constexpr int DONE_RING = 8;                // "tile computed" barriers (see the
 #ifndef LRB_EW20
 #define LRB_EW20 8
 #endif
+#ifndef LRB_ROLE_HIGH
+#define LRB_ROLE_HIGH 0
+#endif
 constexpr int SLOT_PARTS = LRB_EW20 / 4;
 // harness timeline (PROBE builds): clock stamps of CTA 0 for tiles [TL_T0, TL_T0 + TL_N), 24 slots per tile behind the
 // per-CTA counters: {MMA warp woke up, MMA warp committed, 8 x epilogue warp saw "done", 8 x epilogue warp released}
@@ -473,7 +476,16 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* a_empty_bar = a_full_bar + 1;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
 
-  const int warp = threadIdx.x >> 5;
+  // Warp roles by ROLE index: 0 = TMA producer, 1-2 = MMA issuers, 3 = threshold service, 4.. = epilogue.
+  // LRB_ROLE_HIGH = 1 gives the four service roles the HIGHEST warp ids of the CTA (hardware warps EW..EW+3) and the
+  // epilogue the warps 0..EW-1; 0 is the historical order (roles == hardware warp ids).  Epilogue warp ew reads the
+  // TMEM lane quadrant ew % 4 == hardware warp % 4 in either order.
+  const int hw_warp = threadIdx.x >> 5;
+#if LRB_ROLE_HIGH
+  const int warp = hw_warp >= EW ? hw_warp - EW : hw_warp + 4;
+#else
+  const int warp = hw_warp;
+#endif
   const int lane = threadIdx.x & 31;
   const bool has_bias = p.bias_blk != nullptr;
   long long probe_c0 = 0, probe_t0 = 0;

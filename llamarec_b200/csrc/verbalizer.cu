@@ -32,6 +32,7 @@ struct Params {
   const int* word_ids;           // [C][W]
   const unsigned char* word_mask;// [C][W]
   int C, W, mode, round_bf16;
+  const float* calib_logits;     // optional [V] fp32: ManualVerbalizer._calibrate_logits (trainer/verb.py:202-208)
   float* out;                    // [B][C]
 };
 
@@ -47,9 +48,13 @@ LRB_DEVINL void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
 // Verbalizer post-processing for one user, executed by a whole warp (lanes = label words):
 //   project   : logit - 10000 * (1 - word_mask)                          trainer/verb.py:543
 //   normalize : softmax over ALL label words, log(p + 1e-15)   (mode 1)  trainer/verb.py:570-582
+//   calibrate : (mode 1, optional) p /= softmax(project(calibration logits)) + 1e-15, renormalised over all
+//               label words                                             trainer/verb.py:616-643
 //   aggregate : masked mean over the W words of each class               trainer/verb.py:611-614
+// calib_logit = this lane's label-word logit of the calibration vector (same multi-token handler), unused when
+// has_calib is false.
 LRB_DEVINL void verbalizer_tail(int mode, int C, int W, const unsigned char* word_mask, float logit, int lane,
-                                float* out_row) {
+                                float* out_row, bool has_calib = false, float calib_logit = 0.f) {
   const int n_words = C * W;
   float x = -INFINITY;
   float m = 0.f;
@@ -63,7 +68,19 @@ LRB_DEVINL void verbalizer_tail(int mode, int C, int W, const unsigned char* wor
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const float e = lane < n_words ? expf(x - mx) : 0.f;
     const float den = warp_sum(e);
-    x = logf(e / den + 1e-15f);
+    float pr = e / den;
+    if (has_calib) {
+      const float cx = lane < n_words ? calib_logit - 10000.0f * (1.0f - m) : -INFINITY;
+      float cmx = cx;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cmx = fmaxf(cmx, __shfl_xor_sync(0xffffffffu, cmx, o));
+      const float ce = lane < n_words ? expf(cx - cmx) : 0.f;
+      const float cden = warp_sum(ce);
+      pr = pr / (ce / cden + 1e-15f);
+      const float norm = warp_sum(lane < n_words ? pr : 0.f);
+      pr = pr / norm;
+    }
+    x = logf(pr + 1e-15f);
   }
   const float num = lane < n_words ? x * m : 0.f;
   float tot = 0.f, totm = 0.f;
@@ -127,8 +144,14 @@ __global__ void __launch_bounds__(WARPS * 32) verbalizer_kernel(const Params p) 
   const int b = b0 + warp;
   if (b >= p.B) return;
 
+  float cal = 0.f;
+  if (p.calib_logits != nullptr && lane < n_words) {
+    long long tok = p.word_ids[lane];
+    if (tok < 0 || tok >= p.V) tok = 0;
+    cal = __ldg(p.calib_logits + tok);
+  }
   verbalizer_tail(p.mode, p.C, p.W, p.word_mask, lane < n_words ? s_logit[warp][lane] : 0.f, lane,
-                  p.out + static_cast<size_t>(b) * p.C);
+                  p.out + static_cast<size_t>(b) * p.C, p.calib_logits != nullptr, cal);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -145,6 +168,7 @@ struct LogitParams {
   const unsigned char* tok_mask;   // [C][W][T]
   const unsigned char* word_mask;  // [C][W]
   int C, W, T, mode, handler;      // handler 0 = first, 1 = max, 2 = mean
+  const float* calib_logits;       // optional [V] fp32 calibration logits
   float* out;                      // [B][C]
 };
 
@@ -153,9 +177,8 @@ __global__ void __launch_bounds__(WARPS * 32) verbalizer_logits_kernel(const Log
   const int b = blockIdx.x * WARPS + warp;
   if (b >= p.B) return;
   const int n_words = p.C * p.W;
-  float x = 0.f;
-  if (lane < n_words) {
-    const float* row = p.logits + static_cast<size_t>(b) * p.ld;
+  // this lane's label-word logit of one logits row: sub-tokens gathered and reduced by the handler
+  auto word_logit = [&](const float* row) {
     const int* ids = p.tok_ids + lane * p.T;
     const unsigned char* tm = p.tok_mask + lane * p.T;
     auto at = [&](int t) {
@@ -163,23 +186,27 @@ __global__ void __launch_bounds__(WARPS * 32) verbalizer_logits_kernel(const Log
       if (tok < 0 || tok >= p.V) tok = 0;
       return __ldg(row + tok);
     };
-    if (p.handler == 0) {
-      x = at(0);
-    } else if (p.handler == 1) {
+    if (p.handler == 0) return at(0);
+    if (p.handler == 1) {
       float mx = -INFINITY;
       for (int t = 0; t < p.T; ++t) mx = fmaxf(mx, at(t) - 1000.0f * (1.0f - (tm[t] ? 1.f : 0.f)));
-      x = mx;
-    } else {
-      float sum = 0.f, cnt = 0.f;
-      for (int t = 0; t < p.T; ++t) {
-        const float m = tm[t] ? 1.f : 0.f;
-        sum += at(t) * m;
-        cnt += m;
-      }
-      x = sum / (cnt + 1e-15f);
+      return mx;
     }
+    float sum = 0.f, cnt = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      const float m = tm[t] ? 1.f : 0.f;
+      sum += at(t) * m;
+      cnt += m;
+    }
+    return sum / (cnt + 1e-15f);
+  };
+  float x = 0.f, cal = 0.f;
+  if (lane < n_words) {
+    x = word_logit(p.logits + static_cast<size_t>(b) * p.ld);
+    if (p.calib_logits != nullptr) cal = word_logit(p.calib_logits);
   }
-  verbalizer_tail(p.mode, p.C, p.W, p.word_mask, x, lane, p.out + static_cast<size_t>(b) * p.C);
+  verbalizer_tail(p.mode, p.C, p.W, p.word_mask, x, lane, p.out + static_cast<size_t>(b) * p.C,
+                  p.calib_logits != nullptr, cal);
 }
 
 }  // namespace verb
@@ -187,7 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32) verbalizer_logits_kernel(const Log
 
 extern "C" int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head_bf16, int B, int H, int64_t V,
                                     const int32_t* word_ids, const uint8_t* word_mask, int C, int W, int mode,
-                                    int round_bf16, float* out, void* stream) {
+                                    int round_bf16, const float* calib_logits, float* out, void* stream) {
   using namespace lrb;
   int rc = check_arch();
   if (rc != LRB_OK) return rc;
@@ -202,7 +229,7 @@ extern "C" int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head
   p.hidden = static_cast<const __nv_bfloat16*>(hidden_bf16);
   p.lm_head = static_cast<const __nv_bfloat16*>(lm_head_bf16);
   p.B = B; p.H = H; p.V = V; p.word_ids = word_ids; p.word_mask = word_mask;
-  p.C = C; p.W = W; p.mode = mode; p.round_bf16 = round_bf16; p.out = out;
+  p.C = C; p.W = W; p.mode = mode; p.round_bf16 = round_bf16; p.calib_logits = calib_logits; p.out = out;
   const size_t smem = static_cast<size_t>(verb::UB) * H * 2;
   const int grid = (B + verb::UB - 1) / verb::UB;
   const int nvec = H / 256;
@@ -230,7 +257,7 @@ extern "C" int lrb_verbalizer_score(const void* hidden_bf16, const void* lm_head
 
 extern "C" int lrb_verbalizer_from_logits(const float* logits, int64_t ld, int B, int64_t V, const int32_t* tok_ids,
                                           const uint8_t* tok_mask, const uint8_t* word_mask, int C, int W, int T,
-                                          int handler, int mode, float* out, void* stream) {
+                                          int handler, int mode, const float* calib_logits, float* out, void* stream) {
   using namespace lrb;
   int rc = check_arch();
   if (rc != LRB_OK) return rc;
@@ -242,7 +269,8 @@ extern "C" int lrb_verbalizer_from_logits(const float* logits, int64_t ld, int B
     return set_error(LRB_ERR_UNSUPPORTED, "at most %d label words in total (got %d x %d)", verb::MAX_WORDS, C, W);
   verb::LogitParams p;
   p.logits = logits; p.ld = ld; p.B = B; p.V = V; p.tok_ids = tok_ids; p.tok_mask = tok_mask;
-  p.word_mask = word_mask; p.C = C; p.W = W; p.T = T; p.mode = mode; p.handler = handler; p.out = out;
+  p.word_mask = word_mask; p.C = C; p.W = W; p.T = T; p.mode = mode; p.handler = handler;
+  p.calib_logits = calib_logits; p.out = out;
   const int grid = (B + verb::WARPS - 1) / verb::WARPS;
   verb::verbalizer_logits_kernel<<<grid, verb::WARPS * 32, 0, as_stream(stream)>>>(p);
   LRB_CUDA_TRY(cudaGetLastError());

@@ -1,8 +1,9 @@
 """Verbalizer with the reference's interface (trainer/verb.py:420-643, copy in demo/verb.py).
 
 `ManualVerbalizer(tokenizer, classes, label_words, prefix, multi_token_handler, post_log_softmax)` keeps
-the constructor and `process_logits(logits[B, V]) -> [B, C]` (project, handle_multi_token, normalize, log and
-aggregate of trainer/verb.py:524-614 in one kernel, lrb_verbalizer_from_logits).  The fast path is
+the constructor, `register_calibrate_logits` and `process_logits(logits[B, V]) -> [B, C]` (project,
+handle_multi_token, normalize, calibrate, log and aggregate of trainer/verb.py:524-643 in one kernel,
+lrb_verbalizer_from_logits).  The fast path is
 
     score_hidden(hidden_last[B, H], lm_head_weight[V, H]) -> [B, C]
 
@@ -32,8 +33,33 @@ class ManualVerbalizer:
         self.multi_token_handler = multi_token_handler
         self.post_log_softmax = post_log_softmax
         self._label_words = None
+        self._calibrate_logits = None
         if label_words is not None:
             self.label_words = label_words
+
+    # ---- calibration (trainer/verb.py:202-208, 616-643) ---------------------------------------------
+    def register_calibrate_logits(self, logits: Optional[torch.Tensor]) -> None:
+        """Registers the [V] calibration logits (None removes them).  With `post_log_softmax` the label-word
+        probabilities are then divided by the calibration vector's own label-word probabilities (+1e-15) and
+        renormalised over all label words before the log -- `ManualVerbalizer.calibrate` -- inside the same kernel."""
+        if logits is not None:
+            if logits.dim() != 1:
+                raise AssertionError("self._calibrate_logits are not 1-d tensor")       # trainer/verb.py:626-628
+            logits = logits.detach().to(torch.float32).contiguous()
+        self._calibrate_logits = logits
+        if hasattr(self, "_dev_cache"):
+            self._dev_cache = {k: v for k, v in self._dev_cache.items() if not (isinstance(k, tuple) and k[0] == "cal")}
+
+    def _calib_ptr(self, dev, V: int):
+        """Device pointer of the calibration logits (0 = none); they are only consulted in post_log_softmax mode."""
+        if self._calibrate_logits is None or not self.post_log_softmax:
+            return None
+        if self._calibrate_logits.numel() != V:
+            raise ValueError(f"calibration logits have {self._calibrate_logits.numel()} entries, the vocabulary {V}")
+        key = ("cal", str(dev))
+        if key not in self._dev_cache:
+            self._dev_cache[key] = self._calibrate_logits.to(dev)
+        return self._dev_cache[key]
 
     # ---- label words (trainer/verb.py:136-160 setter semantics, :463-522) -------------------------
     @property
@@ -106,10 +132,12 @@ class ManualVerbalizer:
         B, H = h.shape
         C, W = ids.shape
         out = torch.empty(B, C, dtype=torch.float32, device=dev)
+        cal = self._calib_ptr(dev, w.shape[0])
         with _lib.on_device(h):
             _lib.check(lib.lrb_verbalizer_score(_lib.ptr(h), _lib.ptr(w), B, H, w.shape[0], _lib.ptr(ids),
                                                 _lib.ptr(mask), C, W, 1 if self.post_log_softmax else 0,
-                                                1 if round_logits_to_bf16 else 0, _lib.ptr(out),
+                                                1 if round_logits_to_bf16 else 0,
+                                                _lib.ptr(cal) if cal is not None else None, _lib.ptr(out),
                                                 _lib.stream_handle()))
         return out
 
@@ -135,11 +163,13 @@ class ManualVerbalizer:
             B, V = lg.shape
             C, W, T = ids.shape
             out = torch.empty(B, C, dtype=torch.float32, device=dev)
+            cal = self._calib_ptr(dev, V)
             with _lib.on_device(lg):
                 _lib.check(lib.lrb_verbalizer_from_logits(lg.data_ptr(), lg.stride(0), B, V, _lib.ptr(ids),
                                                           _lib.ptr(tmask), _lib.ptr(wmask), C, W, T,
                                                           self._HANDLERS[self.multi_token_handler],
-                                                          1 if self.post_log_softmax else 0, _lib.ptr(out),
+                                                          1 if self.post_log_softmax else 0,
+                                                          _lib.ptr(cal) if cal is not None else None, _lib.ptr(out),
                                                           _lib.stream_handle()))
             return out
         raise RuntimeError("ManualVerbalizer.process_logits needs a CUDA device: project / normalize / aggregate "

@@ -266,6 +266,19 @@ def make_verbalizer_handler_fixture():
                                   pls, handler)
             assert torch.allclose(o, r, atol=1e-6), (handler, pls)
             out[f"{handler}_pls{int(pls)}"] = r.detach().numpy()
+    # calibration (register_calibrate_logits + ManualVerbalizer.calibrate, trainer/verb.py:202-208,616-643)
+    gcal = torch.Generator().manual_seed(11)
+    cal = torch.randn(logits.shape[1], generator=gcal) * 2.0
+    out["calibrate_logits"] = cal.numpy()
+    for handler in ("first", "mean"):
+        rv = verb.ManualVerbalizer(tokenizer=Tok(), prefix="", post_log_softmax=True, classes=classes,
+                                   label_words=lw, multi_token_handler=handler)
+        rv.register_calibrate_logits(cal.clone())
+        r = rv.process_logits(logits.clone())
+        o = VO.process_logits(logits, rv.label_words_ids.data, rv.words_ids_mask.data, rv.label_words_mask.data,
+                              True, handler, calibrate_logits=cal)
+        assert torch.allclose(o, r, atol=1e-5), (handler, float((o - r).abs().max()))
+        out[f"{handler}_calibrated"] = r.detach().numpy()
     np.savez(os.path.join(OUT, "verbalizer_handlers.npz"), **out)
     print("verbalizer handlers ok")
 

@@ -14,6 +14,7 @@ from conftest import CASES, GOLDEN, load_case, metrics_vector
 from llamarec_b200 import LRURec, LRURetriever, ManualVerbalizer, absolute_recall_mrr_ndcg_for_ks, merge_lists, synth
 from oracle import lru_oracle as O
 from oracle import metrics_oracle as MO
+from oracle import verbalizer_oracle as VO
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-3
@@ -193,6 +194,26 @@ def test_verbalizer_kernel_matches_reference():
                                  post_log_softmax=bool(pls), multi_token_handler=handler)
             got = v.process_logits(logits).cpu().numpy()
             np.testing.assert_allclose(got, h[f"{handler}_pls{pls}"], atol=5e-6, rtol=2e-6)
+    # calibration (register_calibrate_logits -> ManualVerbalizer.calibrate, trainer/verb.py:202-208,616-643) against
+    # the reference class, on precomputed logits (first / mean handlers) and through the hidden-state kernel
+    cal = torch.from_numpy(h["calibrate_logits"])
+    for handler in ("first", "mean"):
+        vc = ManualVerbalizer(Tok(), classes=list(range(16)), label_words=lw, prefix="", post_log_softmax=True,
+                              multi_token_handler=handler)
+        vc.register_calibrate_logits(cal)
+        np.testing.assert_allclose(vc.process_logits(logits).cpu().numpy(), h[f"{handler}_calibrated"], atol=2e-5, rtol=1e-5)
+        vc.register_calibrate_logits(None)
+        np.testing.assert_allclose(vc.process_logits(logits).cpu().numpy(), h[f"{handler}_pls1"], atol=5e-6, rtol=2e-6)
+    vh = ManualVerbalizer(Tok(), classes=list(range(20)), label_words={i: chr(ord("A") + i) for i in range(20)},
+                          prefix="", post_log_softmax=True)
+    vh.register_calibrate_logits(cal)
+    lg = torch.nn.functional.linear(hid.float().cpu(), w.float().cpu())
+    want = VO.process_logits(lg, vh.label_words_ids, vh.words_ids_mask, vh.label_words_mask, True, "first",
+                             calibrate_logits=cal)
+    np.testing.assert_allclose(vh.score_hidden(hid, w, round_logits_to_bf16=False).cpu().numpy(), want.numpy(),
+                               atol=2e-4, rtol=RTOL)
+    with pytest.raises(AssertionError):
+        vh.register_calibrate_logits(torch.zeros(2, 3))
     # a non-contiguous view of a wider logits matrix (row pitch > V)
     wide = torch.zeros(logits.shape[0], logits.shape[1] + 37, device="cuda")
     wide[:, :logits.shape[1]] = logits

@@ -130,3 +130,11 @@ def test_oracle_multi_token_handlers_match_reference():
                                  post_log_softmax=bool(pls), multi_token_handler=handler)   # label-word tables only
             o = VO.process_logits(logits, v.label_words_ids, v.words_ids_mask, v.label_words_mask, bool(pls), handler)
             np.testing.assert_allclose(o.numpy(), h[f"{handler}_pls{pls}"], atol=1e-6)
+    # ManualVerbalizer.calibrate (trainer/verb.py:616-643) with registered calibration logits
+    cal = torch.from_numpy(h["calibrate_logits"])
+    for handler in ("first", "mean"):
+        v = ManualVerbalizer(Tok(), classes=list(range(16)), label_words=lw, prefix="", post_log_softmax=True,
+                             multi_token_handler=handler)
+        o = VO.process_logits(logits, v.label_words_ids, v.words_ids_mask, v.label_words_mask, True, handler,
+                              calibrate_logits=cal)
+        np.testing.assert_allclose(o.numpy(), h[f"{handler}_calibrated"], atol=1e-5)
