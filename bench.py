@@ -507,10 +507,13 @@ def run_product(args, rank, world, local_rank):
     peak_tf = pk["bf16_tflops_sustained"] if peak_kind == "sustained" else pk["bf16_tflops"]
     step_flops = flops
     traffic = None
+    traffic_source = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("score_topk_tc_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("score_topk_tc_dram_bytes_per_launch")
+            traffic_source = tj.get("source")
         except (ValueError, OSError):
             traffic = None
     line = {
@@ -539,6 +542,7 @@ def run_product(args, rank, world, local_rank):
         "gpu_launches": args.steps * (1 + 6 + score_launches + 1 + (1 if world > 1 else 0) + (1 if weak else 0)),
         "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                     "traffic_source": traffic_source,
                      "peak_source": f"{pk['source']} ({peak_kind} bf16: the timed region lasted {region_s:.2f} s)",
                      "frac_of_burst": achieved / pk["bf16_tflops"],
                      "frac_of_sustained": achieved / pk["bf16_tflops_sustained"],

@@ -274,6 +274,7 @@ struct ScanParams {
 };
 
 constexpr int MAX_LEVELS = 8;   // LRB_MAX_LEN = 256
+constexpr int SCAN_CHUNK = 8;   // time steps whose loads are in flight together
 
 __global__ void __launch_bounds__(128) lru_scan_kernel(const ScanParams p) {
   __shared__ unsigned char s_mask[LRB_MAX_LEN];
@@ -291,40 +292,51 @@ __global__ void __launch_bounds__(128) lru_scan_kernel(const ScanParams p) {
 #pragma unroll
   for (int l = 0; l < MAX_LEVELS; ++l) { qr[l] = 0.f; qi[l] = 0.f; }
 
+  // Time is walked in chunks of SCAN_CHUNK steps: the chunk's bu values are requested together (independent
+  // 8-byte loads, one 1 KB row per step across the CTA), then the recurrence runs over registers and the states are
+  // written back.  With a mean of ~9 real tokens per user the kernel is latency-bound, not bandwidth-bound: one
+  // chunk puts SCAN_CHUNK rows in flight per thread instead of the single prefetched row of the first version.
   float2* row = p.bu + static_cast<size_t>(base) * LRB_H + c;
-  float2 nxt = n > 0 ? row[0] : make_float2(0.f, 0.f);
-  for (int j = 0; j < n; ++j) {
-    const float2 cur = nxt;
-    if (j + 1 < n) nxt = row[static_cast<size_t>(j + 1) * LRB_H];
-    const int t = first + j;
-    const int pos = t + off;
-    float ar = cur.x, ai = cur.y;
-    float sr = 0.f, si = 0.f;
-    int zlev = -1;
-    bool below_all_ones = true;
+  for (int j0 = 0; j0 < n; j0 += SCAN_CHUNK) {
+    float2 v[SCAN_CHUNK];
 #pragma unroll
-    for (int l = 0; l < MAX_LEVELS; ++l) {
-      if (l < p.levels) {
-        const bool bit = (pos >> l) & 1;
-        if (bit) {
-          ar += qr[l];
-          ai += qi[l];
-        } else if (below_all_ones) {
-          sr = ar; si = ai; zlev = l;     // H_l(pos): value after the levels below l only
-          below_all_ones = false;
+    for (int u = 0; u < SCAN_CHUNK; ++u)
+      v[u] = (j0 + u < n) ? row[static_cast<size_t>(j0 + u) * LRB_H] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < SCAN_CHUNK; ++u) {
+      const int j = j0 + u;
+      if (j < n) {
+        const int t = first + j;
+        const int pos = t + off;
+        float ar = v[u].x, ai = v[u].y;
+        float sr = 0.f, si = 0.f;
+        int zlev = -1;
+        bool below_all_ones = true;
+#pragma unroll
+        for (int l = 0; l < MAX_LEVELS; ++l) {
+          if (l < p.levels) {
+            const bool bit = (pos >> l) & 1;
+            if (bit) {
+              ar += qr[l];
+              ai += qi[l];
+            } else if (below_all_ones) {
+              sr = ar; si = ai; zlev = l;     // H_l(pos): value after the levels below l only
+              below_all_ones = false;
+            }
+          }
         }
-      }
-    }
-    if (!p.last_only) row[static_cast<size_t>(j) * LRB_H] = make_float2(ar, ai);
-    else if (j == n - 1) p.h_last[static_cast<size_t>(b) * LRB_H + c] = make_float2(ar, ai);
-    const float m = s_mask[t] ? 1.f : 0.f;
+        if (!p.last_only) row[static_cast<size_t>(j) * LRB_H] = make_float2(ar, ai);
+        else if (j == n - 1) p.h_last[static_cast<size_t>(b) * LRB_H + c] = make_float2(ar, ai);
+        const float m = s_mask[t] ? 1.f : 0.f;
 #pragma unroll
-    for (int l = 0; l < MAX_LEVELS; ++l) {
-      if (l < p.levels) {
-        float xr = qr[l], xi = qi[l];
-        if (l == zlev) { xr = sr * m; xi = si * m; }
-        qr[l] = xr * lr - xi * li;
-        qi[l] = xr * li + xi * lr;
+        for (int l = 0; l < MAX_LEVELS; ++l) {
+          if (l < p.levels) {
+            float xr = qr[l], xi = qi[l];
+            if (l == zlev) { xr = sr * m; xi = si * m; }
+            qr[l] = xr * lr - xi * li;
+            qi[l] = xr * li + xi * lr;
+          }
+        }
       }
     }
   }

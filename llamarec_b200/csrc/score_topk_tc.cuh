@@ -43,6 +43,9 @@ constexpr int DONE_RING = 8;                // "tile computed" barriers (see the
 #ifndef LRB_ROLE_HIGH
 #define LRB_ROLE_HIGH 0
 #endif
+#ifndef LRB_MMA_POLL1
+#define LRB_MMA_POLL1 0
+#endif
 constexpr int SLOT_PARTS = LRB_EW20 / 4;
 // harness timeline (PROBE builds): clock stamps of CTA 0 for tiles [TL_T0, TL_T0 + TL_N), 24 slots per tile behind the
 // per-CTA counters: {MMA warp woke up, MMA warp committed, 8 x epilogue warp saw "done", 8 x epilogue warp released}
@@ -618,6 +621,17 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int stage = t % NS;
           {
             const long long w0 = PROBE != 0 ? clock64() : 0;
+#if LRB_MMA_POLL1
+            // one lane, two waits in a row: the accumulator stage (normally the later event) first
+            if (lane == 0) {
+              mbar_wait(&tmem_empty_bar[mw], static_cast<uint32_t>(((t >> 1) & 1) ^ 1));
+              if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+                p.probe_out[TL_BASE + (t - TL_T0) * 24 + 19] = clock64();
+              mbar_wait(&full_bar[stage], static_cast<uint32_t>((t / NS) & 1));
+              if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+                p.probe_out[TL_BASE + (t - TL_T0) * 24 + 18] = clock64();
+            }
+#else
             if (lane < 2) {
               uint64_t* bar = lane == 0 ? &full_bar[stage] : &tmem_empty_bar[mw];
               const uint32_t par = lane == 0 ? static_cast<uint32_t>((t / NS) & 1) : static_cast<uint32_t>(((t >> 1) & 1) ^ 1);
@@ -625,6 +639,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
               if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
                 p.probe_out[TL_BASE + (t - TL_T0) * 24 + 18 + lane] = clock64();   // operands landed / stage drained
             }
+#endif
             __syncwarp();
             if (PROBE != 0) probe_wait += clock64() - w0;
             if (PROBE != 0 && blockIdx.x == 0 && lane == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)

@@ -111,7 +111,7 @@ class LRURec(nn.Module):
         self.model.lru_blocks = nn.ModuleList(blocks)
         self.model.bias = nn.Parameter(torch.zeros(vocab))
         for name, p in self.named_parameters():
-            if "layer_norm" in name or "params_log" in name or name == "model.bias":
+            if "layer_norm" in name or "params_log" in name:     # model/lru.py:21 -- model.bias IS initialised
                 continue
             if torch.is_complex(p):
                 with torch.no_grad():
