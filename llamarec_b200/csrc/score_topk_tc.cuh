@@ -10,14 +10,17 @@
 //         16-score group to a ring; rings are drained warp-wide (lock-step) into per-thread top-K sets.
 // The B x N score matrix never leaves the SM.
 //
-// Tile: 128 users (TMEM lanes) x 256 items (TMEM columns) x K=64 per CTA; two TMEM accumulator stages.
+// Tile: 128 users (TMEM lanes) x 256 items x K=64 per CTA, staged in shared memory as one TMA tile and computed as
+// two N = 128 half-tiles; FOUR TMEM accumulator stages of 128 columns.
 // CG = 2 (every launch with more than one user tile): two CTAs of a TPC form a pair (cluster of 2,
 // tcgen05 cta_group::2) that shares each 256-item tile -- every CTA stages only its 128 item rows, the leader
-// issues M = 256 MMAs, both CTAs read their own 128 x 256 accumulators out of their own TMEM.
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM
-// allocator, warp 3 = builds the "ones" block, then threshold service (union bound), warps 4..11 = epilogue
-// (warp w reads TMEM lanes 32*(w%4).., column half (w-4)/4).  The bias is folded into the GEMM as a fifth
-// K=16 MMA per tile.  Consecutive launches of one call (user chunks) overlap via programmatic dependent launch.
+// issues M = 256 MMAs, both CTAs read their own 128-lane accumulators out of their own TMEM.
+// Warp roles (384 threads): warp 0 = TMA producer, warps 1-2 = MMA issuers (leader CTA only; even / odd tiles),
+// warp 2 also allocates TMEM, warp 3 = builds the "ones" block, then threshold service (union bound),
+// warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4).., 64 of the 128 columns of every half-tile).  The
+// producer / MMA / service warpgroup gives registers to the epilogue warpgroups (setmaxnreg 56 / 224).  The bias is
+// folded into the GEMM as a fifth K=16 MMA per half-tile.  Consecutive launches of one call (user chunks) overlap via
+// programmatic dependent launch.
 #pragma once
 
 #include <cuda.h>
@@ -31,24 +34,26 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
-constexpr int ACC_STAGES = 2;               // two 256-column fp32 accumulators fill the SM's 512 TMEM columns
-constexpr int TMEM_COLS = ACC_STAGES * BN;
-constexpr int DONE_RING = 8;                // "tile computed" barriers (see the kernel); must exceed the TMA ring depth
+// Accumulators: the SM's 512 TMEM columns hold FOUR stages of 128 columns; a 256-item tile is computed as two
+// N = 128 half-tiles.  With two 256-column stages the loop  release -> MMA -> commit -> read-out  ran ~1040 cycles per
+// tile although the tensor pipe needs 512 and the read-out ~700: the hand-offs between the MMA-issuing thread and the
+// epilogue warps (mbarrier round trips, remote arrivals of the pair's other CTA, MMA issue) add ~900 cycles to every
+// stage cycle and only two stages were in flight to hide them (B200, tools/tc_check per-CTA counters: the epilogue
+// warps AND the MMA warps waited for each other).  Four half-size stages double the work in flight.
+constexpr int HN = 128;                     // accumulator columns per half-tile
+constexpr int ACC_STAGES = 4;
+constexpr int TMEM_COLS = ACC_STAGES * HN;
+constexpr int DONE_RING = 8;                // tiles in the ring of "half-tile computed" barriers (two per tile); must exceed the TMA ring depth
 // Epilogue warps of the K <= 20 kernel: 8 (two 128-column parts per tile) or 16 (four 64-column parts).  Measured on
 // B200 (10M rows, 4096 users): 16 warps read the accumulators a little faster in isolation (tools/epi_probe: 702 vs 757
 // cycles per tile) but lose in the kernel (96 registers per thread, twice the per-thread candidate sets): 5.86 vs 5.25 ms.
 #ifndef LRB_EW20
 #define LRB_EW20 8
 #endif
-#ifndef LRB_ROLE_HIGH
-#define LRB_ROLE_HIGH 0
-#endif
-#ifndef LRB_MMA_POLL1
-#define LRB_MMA_POLL1 0
-#endif
 constexpr int SLOT_PARTS = LRB_EW20 / 4;
 // harness timeline (PROBE builds): clock stamps of CTA 0 for tiles [TL_T0, TL_T0 + TL_N), 24 slots per tile behind the
-// per-CTA counters: {MMA warp woke up, MMA warp committed, 8 x epilogue warp saw "done", 8 x epilogue warp released}
+// per-CTA counters: {MMA warp woke up, MMA warp committed the second half-tile, 8 x epilogue warp saw the first
+// half-tile done, 8 x epilogue warp released the second half-tile, operands landed, first stage drained}
 constexpr int TL_T0 = 2000, TL_N = 16, TL_BASE = 148 * 8;    // partial-list / union-bound slots reserved per stream (>= column parts)
 
 struct ScoreParams {
@@ -400,8 +405,8 @@ struct SmemLayout {
   static constexpr int kRowThr = kListN + kEpiThreads * 8;
   static constexpr int kExcl = kRowThr + 2 * BM * 4 + 16;   // two threshold buffers + service-warp flags
   static constexpr int kBars = kExcl + (kExclSmem ? BM * EX_CAP * 4 : 0);
-  // barriers: full[NS], done[DONE_RING], tmem_empty[2], a_full, a_empty
-  static constexpr int kNumBars = NS + DONE_RING + ACC_STAGES + 2;
+  // barriers: full[NS], done[DONE_RING][2], tmem_empty[ACC_STAGES], a_full, a_empty
+  static constexpr int kNumBars = NS + 2 * DONE_RING + ACC_STAGES + 2;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
   static constexpr int kAlloc = kTotal + 1024;  // slack for manual 1024-B alignment
@@ -432,14 +437,15 @@ LRB_DEVINL uint64_t umma_desc_k16_sw32(uint32_t smem_addr) {
 //
 // Synchronisation (mbarriers; "tile" = one 256-item tile of one segment, counted per CTA in issue order):
 //   full[s]        TMA bytes of shared-memory stage s have landed            producer -> MMA warp
-//   done[t % 8]    the MMAs of tile t have completed (ONE tcgen05.commit per tile):
-//                  the accumulator stage t % 2 is full                       MMA -> epilogue warps (both CTAs of a pair)
-//                  AND shared-memory stage t % NS may be refilled            MMA -> TMA producer(s)
+//   done[t % 8][h] the MMAs of half-tile h of tile t have completed (one tcgen05.commit per half-tile):
+//                  the accumulator stage (t & 1) * 2 + h is full            MMA -> epilogue warps (both CTAs of a pair)
+//                  h == 1: AND shared-memory stage t % NS may be refilled    MMA -> TMA producer(s)
 //   tmem_empty[a]  every epilogue warp has read accumulator stage a          epilogue -> MMA warp
-// The MMA-issuing thread is the one serial resource of the pipeline: whatever it spends between two tiles that is
-// not `tcgen05.mma` shows up as idle tensor-pipe cycles (measured, tools/tmem_probe modes 8-10: a second commit per
-// tile costs 80-130 cycles, a second barrier wait ~120).  Hence one commit per tile, and the two things it has to
-// wait for (operands landed, accumulator stage drained) are polled by two lanes of the MMA warp in ONE try_wait.
+// What bounds this kernel is the LATENCY of that loop, not a pipe (harness timeline, tools/tc_check with
+// LRB_TIMELINE=1): from "stage released" to "its next accumulator seen by the epilogue" pass
+// ~1500 cycles of hand-offs (remote mbarrier arrivals of the pair's other CTA, the MMA warp's wake-up and issue, the
+// commit's arrival) on top of the MMA itself; throughput = TMEM columns in flight / that cycle, hence four small
+// stages instead of two large ones, and every hand-off kept as short as it goes.
 template <int KMAX, int NS, bool kDense, int CG, int EW, int CMAX = MAX_C_SHARE_SMALL, int PROBE = 0>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -447,12 +453,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_bias, const ScoreParams p) {
   using L = SmemLayout<KMAX, NS, CG, EW>;
   static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
-  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+  static_assert(EW == 8, "8 epilogue warps: two 128-column parts per tile (16 warps measured slower, see above)");
   constexpr int EPI_THREADS = EW * 32;
   constexpr int MAX_C_SHARE = CMAX;
   constexpr int PARTS = EW / 4;            // column parts of a tile
-  constexpr int COLS = BN / PARTS;         // columns per epilogue thread and tile (128 or 64)
-  constexpr int CH = COLS / 32;            // x32 TMEM loads per thread and tile (4 or 2)
   static_assert(PARTS <= SLOT_PARTS, "slot stride too small");
   // CTA pair: cluster rank 0 leads (issues the MMAs, owns the barriers the pair synchronises on);
   // the pair walks the segments of "pair index" blockIdx.x / 2 and CTA `rank` owns user tile 2*m + rank.
@@ -474,21 +478,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
   uint64_t* full_bar = bars;
   uint64_t* done_bar = bars + NS;
-  uint64_t* tmem_empty_bar = bars + NS + DONE_RING;
-  uint64_t* a_full_bar = bars + NS + DONE_RING + ACC_STAGES;
+  uint64_t* tmem_empty_bar = bars + NS + 2 * DONE_RING;
+  uint64_t* a_full_bar = bars + NS + 2 * DONE_RING + ACC_STAGES;
   uint64_t* a_empty_bar = a_full_bar + 1;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
 
-  // Warp roles by ROLE index: 0 = TMA producer, 1-2 = MMA issuers, 3 = threshold service, 4.. = epilogue.
-  // LRB_ROLE_HIGH = 1 gives the four service roles the HIGHEST warp ids of the CTA (hardware warps EW..EW+3) and the
-  // epilogue the warps 0..EW-1; 0 is the historical order (roles == hardware warp ids).  Epilogue warp ew reads the
-  // TMEM lane quadrant ew % 4 == hardware warp % 4 in either order.
-  const int hw_warp = threadIdx.x >> 5;
-#if LRB_ROLE_HIGH
-  const int warp = hw_warp >= EW ? hw_warp - EW : hw_warp + 4;
-#else
-  const int warp = hw_warp;
-#endif
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool has_bias = p.bias_blk != nullptr;
   long long probe_c0 = 0, probe_t0 = 0;
@@ -507,7 +502,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NS; ++i) mbar_init(&full_bar[i], 1);
-    for (int i = 0; i < DONE_RING; ++i) mbar_init(&done_bar[i], 1);
+    for (int i = 0; i < 2 * DONE_RING; ++i) mbar_init(&done_bar[i], 1);
     for (int i = 0; i < ACC_STAGES; ++i) mbar_init(&tmem_empty_bar[i], EW * CG);   // pair: both CTAs' epilogues arrive on the leader's
     mbar_init(a_full_bar, 1);
     mbar_init(a_empty_bar, 2);   // one commit from each MMA-issuing warp
@@ -541,6 +536,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
+  // Register budget: the kernel is launched with 168 registers per thread (384 threads); the producer / MMA /
+  // service warpgroup keeps 56 and hands the rest to the two epilogue warpgroups (224 each: two 64-register TMEM
+  // load buffers plus the filter state).  128 * 56 + 256 * 224 = 64512 = 384 * 168.
+  if (warp < 4) {
+  setmaxnreg_dec<56>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -567,7 +567,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int it = -n_scout; it < sg.n1 - sg.n0; ++it, ++t) {
           const int n = it < 0 ? sg.n1 + it : sg.n0 + it;   // scout pass re-visits the segment's last tiles
           // stage t % NS was last read by the MMAs of tile t - NS
-          if (t >= NS) mbar_wait(&done_bar[(t - NS) % DONE_RING], ((t - NS) / DONE_RING) & 1);
+          if (t >= NS) mbar_wait(&done_bar[((t - NS) % DONE_RING) * 2 + 1], ((t - NS) / DONE_RING) & 1);
           if (PROBE == 4 && t >= NS) {
             // probe: the stage still holds an item tile -- hand it to the MMA again, no TMA traffic
             if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
@@ -595,22 +595,28 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1 || warp == 2) {
     // ===================== MMA issuers =====================
-    // TWO issuing warps, one per accumulator stage: warp 1 takes the even tiles, warp 2 the odd ones.  An issuing
+    // TWO issuing warps, each with two of the four accumulator stages: warp 1 takes the even tiles, warp 2 the odd
+    // ones; a tile is issued as two N = 128 half-tiles, each with its own stage and its own commit.  An issuing
     // thread is blocked in `tcgen05.mma` while the tensor pipe is busy and only then gets to its commit, its next
     // barrier waits and its descriptor arithmetic -- with a single issuer that gap (~150 cycles per tile) was idle
     // tensor-pipe time (MMA-only probe: 665-685 cycles per tile against 512 for back-to-back MMAs); with two, one
     // warp's gap hides behind the other's MMAs.  In each warp lane 0 polls "operands landed" and lane 1
     // "accumulator stage drained" with ONE try_wait instruction; lane 0 issues.
     if (cta_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
-      const int mw = warp - 1;        // == the accumulator stage this warp owns
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, HN);
+      const int mw = warp - 1;        // this warp owns the accumulator stages 2*mw (first half-tile) and 2*mw+1
       SegmentWalk walk(p, walk_id);
       Segment sg;
       int seg_idx = 0;
       int t = 0;
       const uint64_t desc_a0 = umma_desc_k_sw128(smem_u32(sA));
       const uint64_t desc_ones = umma_desc_k16_sw32(smem_u32(sOnes));
-      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(mw * BN);
+      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(mw * 2 * HN);
+      // Half-tile h of a tile = item rows [h*64, h*64+64) of EACH CTA's 128-row part of the pair's tile (single CTAs:
+      // rows [h*128, h*128+128) of the whole tile): offsets of the B operand / bias block inside a shared-memory stage
+      constexpr uint32_t kHalfRows = HN / CG;
+      constexpr uint32_t kHalfB = kHalfRows * BK * 2;        // bytes (whole SWIZZLE_128B atoms of 8 rows)
+      constexpr uint32_t kHalfBias = kHalfRows * 32;         // bytes (whole SWIZZLE_32B atoms of 8 rows)
       long long probe_wait = 0;
       while (walk.next(sg)) {
         if (lane == 0) mbar_wait(a_full_bar, seg_idx & 1);
@@ -619,27 +625,20 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int t_end = t + n_scout + (sg.n1 - sg.n0);
         for (t += (t & 1) ^ mw; t < t_end; t += 2) {   // this warp's tiles of the segment
           const int stage = t % NS;
+          const uint32_t epar = static_cast<uint32_t>(((t >> 1) & 1) ^ 1);   // this warp's stages: used once per own tile
           {
             const long long w0 = PROBE != 0 ? clock64() : 0;
-#if LRB_MMA_POLL1
-            // one lane, two waits in a row: the accumulator stage (normally the later event) first
+            // one lane, two waits in a row -- the accumulator stage (normally the later event) first.  (Two lanes
+            // polling one barrier each in a single try_wait left ~450 cycles between the later lane's success and the
+            // first MMA: harness timeline, A/B on B200 4.98 -> 4.78 ms at 4096 x 10M.)
             if (lane == 0) {
-              mbar_wait(&tmem_empty_bar[mw], static_cast<uint32_t>(((t >> 1) & 1) ^ 1));
+              mbar_wait(&tmem_empty_bar[2 * mw], epar);
               if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
                 p.probe_out[TL_BASE + (t - TL_T0) * 24 + 19] = clock64();
               mbar_wait(&full_bar[stage], static_cast<uint32_t>((t / NS) & 1));
               if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
                 p.probe_out[TL_BASE + (t - TL_T0) * 24 + 18] = clock64();
             }
-#else
-            if (lane < 2) {
-              uint64_t* bar = lane == 0 ? &full_bar[stage] : &tmem_empty_bar[mw];
-              const uint32_t par = lane == 0 ? static_cast<uint32_t>((t / NS) & 1) : static_cast<uint32_t>(((t >> 1) & 1) ^ 1);
-              mbar_wait(bar, par);
-              if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
-                p.probe_out[TL_BASE + (t - TL_T0) * 24 + 18 + lane] = clock64();   // operands landed / stage drained
-            }
-#endif
             __syncwarp();
             if (PROBE != 0) probe_wait += clock64() - w0;
             if (PROBE != 0 && blockIdx.x == 0 && lane == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
@@ -648,25 +647,37 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (lane == 0) {
             tc_fence_after();
             const uint32_t st = smem_u32(sB + stage * L::kStage);
-            const uint64_t desc_b0 = umma_desc_k_sw128(st);
-            if (PROBE != 2) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                // advance 32 bytes (16 bf16) along K inside the 128-B swizzle atom: +2 in 16-B units
-                if (CG == 2) umma_bf16_ss_pair(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
-                else umma_bf16_ss(d_addr, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1) {   // second accumulator stage of this tile
+                const long long w0 = PROBE != 0 ? clock64() : 0;
+                mbar_wait(&tmem_empty_bar[2 * mw + 1], epar);
+                if (PROBE != 0) probe_wait += clock64() - w0;
+                tc_fence_after();
               }
-              // folded bias: D += ones[128x16] * bias_blk[256x16]^T  (hi + mid + lo bf16 terms)
-              if (has_bias) {
-                if (CG == 2) umma_bf16_ss_pair(d_addr, desc_ones, umma_desc_k16_sw32(st + L::kBBytes), idesc, 1u);
-                else umma_bf16_ss(d_addr, desc_ones, umma_desc_k16_sw32(st + L::kBBytes), idesc, 1u);
+              const uint64_t desc_b0 = umma_desc_k_sw128(st + h * kHalfB);
+              const uint32_t d_h = d_addr + static_cast<uint32_t>(h * HN);
+              if (PROBE != 2) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  // advance 32 bytes (16 bf16) along K inside the 128-B swizzle atom: +2 in 16-B units
+                  if (CG == 2) umma_bf16_ss_pair(d_h, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+                  else umma_bf16_ss(d_h, desc_a0 + 2 * k, desc_b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+                }
+                // folded bias: D += ones[128x16] * bias_blk[128x16]^T  (hi + mid + lo bf16 terms)
+                if (has_bias) {
+                  const uint64_t desc_bias = umma_desc_k16_sw32(st + L::kBBytes + h * kHalfBias);
+                  if (CG == 2) umma_bf16_ss_pair(d_h, desc_ones, desc_bias, idesc, 1u);
+                  else umma_bf16_ss(d_h, desc_ones, desc_bias, idesc, 1u);
+                }
               }
+              // one commit per half-tile: accumulator stage full (epilogues); the second one also means
+              // "shared-memory stage free" (producers)
+              if (CG == 2) umma_commit_pair(&done_bar[(t % DONE_RING) * 2 + h], 0b11);
+              else umma_commit(&done_bar[(t % DONE_RING) * 2 + h]);
+              if (PROBE != 0 && h == 1 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
+                p.probe_out[TL_BASE + (t - TL_T0) * 24 + 1] = clock64();
             }
-            // ONE commit: "tile t computed" = accumulator full (epilogues) + shared-memory stage free (producers)
-            if (CG == 2) umma_commit_pair(&done_bar[t % DONE_RING], 0b11);
-            else umma_commit(&done_bar[t % DONE_RING]);
-            if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
-              p.probe_out[TL_BASE + (t - TL_T0) * 24 + 1] = clock64();
           }
           __syncwarp();
         }
@@ -709,7 +720,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __nanosleep(2000);
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    setmaxnreg_inc<224>();
     // ===================== epilogue =====================
     const int ew = warp - 4;          // 0..EW-1
     const int quad = ew & 3;          // TMEM lane quadrant == warp % 4
@@ -729,27 +742,38 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t acc_empty_addr0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
     const uint32_t peer_drain_addr =
         CG == 2 ? mapa_u32(smem_u32(const_cast<int*>(&sSvc[3])), cta_rank ^ 1u) : 0u;
-    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(part * COLS);
-    auto wait_tile = [&]() {   // the accumulator of tile t is complete
+    // Half-tile h of tile tt lives in accumulator stage (tt & 1) * 2 + h; this warp reads its HCOLS = 64 columns
+    // [part * 64, part * 64 + 64) of every half-tile.  Column c of half-tile h holds the item
+    //     pair:   (c / 64) * 128 + h * 64 + c % 64   (columns 0..63 come from the leader CTA's item rows, 64..127 from the peer's)
+    //     single: h * 128 + c
+    // of the 256-item tile, i.e. this warp's columns are 64 consecutive items starting at item_off(h).
+    constexpr int HCOLS = HN / PARTS;   // 64
+    static_assert(HCOLS == 64, "one tcgen05.ld.32x32b.x64 per warp and half-tile");
+    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(part * HCOLS);
+    auto half_taddr = [&](int tt, int h) { return taddr_lane + static_cast<uint32_t>(((tt & 1) * 2 + h) * HN); };
+    auto item_off = [&](int h) { return CG == 2 ? part * 128 + h * 64 : h * 128 + part * 64; };
+    auto wait_half = [&](int tt, int h) {   // the accumulator of half-tile h of tile tt is complete
+      uint64_t* bar = &done_bar[(tt % DONE_RING) * 2 + h];
       if (PROBE != 0) {
         const long long w0 = clock64();
-        mbar_wait(&done_bar[t % DONE_RING], (t / DONE_RING) & 1);
+        mbar_wait(bar, (tt / DONE_RING) & 1);
         probe_epi_wait += clock64() - w0;
-        if (blockIdx.x == 0 && lane == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
-          p.probe_out[TL_BASE + (t - TL_T0) * 24 + 2 + ew] = clock64();
+        if (h == 0 && blockIdx.x == 0 && lane == 0 && p.probe_out != nullptr && tt >= TL_T0 && tt < TL_T0 + TL_N)
+          p.probe_out[TL_BASE + (tt - TL_T0) * 24 + 2 + ew] = clock64();
       } else {
-        mbar_wait(&done_bar[t % DONE_RING], (t / DONE_RING) & 1);
+        mbar_wait(bar, (tt / DONE_RING) & 1);
       }
       tc_fence_after();
     };
-    auto release_tile = [&]() {   // every load of tile t's accumulator has landed in this warp's registers
+    auto release_half = [&](int tt, int h) {   // this warp's loads of that accumulator stage have landed in its registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {            // (consecutive mbarriers are 8 bytes apart, in either address window)
-        if (CG == 2) mbar_arrive_cluster(acc_empty_addr0 + static_cast<uint32_t>(t % ACC_STAGES) * 8u);
-        else mbar_arrive(&tmem_empty_bar[t % ACC_STAGES]);
-        if (PROBE != 0 && blockIdx.x == 0 && p.probe_out != nullptr && t >= TL_T0 && t < TL_T0 + TL_N)
-          p.probe_out[TL_BASE + (t - TL_T0) * 24 + 10 + ew] = clock64();
+        const uint32_t stg = static_cast<uint32_t>((tt & 1) * 2 + h);
+        if (CG == 2) mbar_arrive_cluster(acc_empty_addr0 + stg * 8u);
+        else mbar_arrive(&tmem_empty_bar[stg]);
+        if (PROBE != 0 && h == 1 && blockIdx.x == 0 && p.probe_out != nullptr && tt >= TL_T0 && tt < TL_T0 + TL_N)
+          p.probe_out[TL_BASE + (tt - TL_T0) * 24 + 10 + ew] = clock64();
       }
     };
     while (walk.next(sg)) {
@@ -808,31 +832,30 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
         for (int j = 0; j < MAX_C_SHARE; ++j) tm[j] = -INFINITY;
         for (int it = 0; it < n_scout_run; ++it, ++t) {
-          wait_tile();
-          if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
-            release_tile();
-            continue;
-          }
-          // Columns past the end of the table (the ragged last tile) must not count as admissible items:
-          // without a folded-bias block they score exactly 0 (TMA zero-fills out-of-bounds rows), and a
-          // bound published from them could exceed a user's true K-th best.  valid = real columns of
-          // this thread's COLS-column part in this tile (warp-uniform; < COLS only for the last tile).
-          const int valid = p.rows - ((sg.n1 - n_scout_run + it) * BN + part * COLS);
-          const uint32_t taddr = taddr_lane + static_cast<uint32_t>((t % ACC_STAGES) * BN);
-          uint32_t w[2][32];
-          tmem_ld_32x32(taddr, w[0]);
-          tmem_ld_wait();
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            wait_half(t, h);
+            if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
+              release_half(t, h);
+              continue;
+            }
+            // Columns past the end of the table (the ragged last tile) must not count as admissible items:
+            // without a folded-bias block they score exactly 0 (TMA zero-fills out-of-bounds rows), and a
+            // bound published from them could exceed a user's true K-th best.  valid = real items among
+            // this thread's 64 columns of the half-tile (warp-uniform; < 64 only in the last tile).
+            const int valid = p.rows - ((sg.n1 - n_scout_run + it) * BN + item_off(h));
+            uint32_t w[64];
+            tmem_ld_32x64(half_taddr(t, h), w);
+            tmem_ld_wait();
+            release_half(t, h);
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            if (c < CH - 1) tmem_ld_32x32(taddr + (c + 1) * 32, w[(c + 1) & 1]);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < 4; ++g) {
               float q[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(w[c & 1][g * 16 + j]);
-              if (valid < COLS) {
+              for (int j = 0; j < 16; ++j) q[j] = __uint_as_float(w[g * 16 + j]);
+              if (valid < HCOLS) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) q[j] = (c * 32 + g * 16 + j < valid) ? q[j] : -INFINITY;
+                for (int j = 0; j < 16; ++j) q[j] = (g * 16 + j < valid) ? q[j] : -INFINITY;
               }
               const float m1 = max3(q[0], q[1], q[2]);
               const float m2 = max3(q[3], q[4], q[5]);
@@ -847,9 +870,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tm[j] = hi;
               }
             }
-            if (c < CH - 1) tmem_ld_wait();
           }
-          release_tile();
         }
         if (live && publishes && n_scout > 0) {
           // E = excluded ids that fall inside the scouted id range (any column part)
@@ -909,129 +930,129 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t rowthr_s = smem_u32(rowthr + r);
       const uint32_t drain_seq_s = smem_u32(const_cast<int*>(&sSvc[3]));
 
-      // hot path per 32 columns: two FMNMX3 trees, ONE compare against the thread's threshold; a group whose
-      // maximum passes is not inspected, it is dumped into the thread's ring (5 stores)
-      auto filter_chunk = [&](const uint32_t (&x)[32], float t_eff, int gid0) {
-        float gmax[2];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float qv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) qv[j] = __uint_as_float(x[g * 16 + j]);
-          const float m1 = max3(qv[0], qv[1], qv[2]);
-          const float m2 = max3(qv[3], qv[4], qv[5]);
-          const float m3 = max3(qv[6], qv[7], qv[8]);
-          const float m4 = max3(qv[9], qv[10], qv[11]);
-          const float m5 = max3(qv[12], qv[13], qv[14]);
-          gmax[g] = fmaxf(max3(m1, m2, m3), max3(m4, m5, qv[15]));
+      if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue (harness)
+        for (int n = sg.n0; n < sg.n1; ++n, ++t) {
+          wait_half(t, 0);
+          release_half(t, 0);
+          wait_half(t, 1);
+          release_half(t, 1);
         }
-        if (fmaxf(gmax[0], gmax[1]) >= t_eff) {   // one branch per 32 columns; the group split happens inside it
+      } else if (kDense) {
+        for (int n = sg.n0; n < sg.n1; ++n, ++t) {
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            wait_half(t, h);
+            uint32_t v[64];
+            tmem_ld_32x64(half_taddr(t, h), v);
+            tmem_ld_wait();
+            release_half(t, h);
+            const int row = m_own * BM + r;
+            const int col0 = n * BN + item_off(h);
+            if (row < p.B) {
+              float* dstp = p.dense_out + static_cast<size_t>(row) * p.dense_ld + col0;
+              if (col0 + HCOLS <= p.rows && (p.dense_ld & 3) == 0) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (gmax[g] >= t_eff) {
+                for (int j = 0; j < HCOLS / 4; ++j)
+                  reinterpret_cast<float4*>(dstp)[j] =
+                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < HCOLS; ++j)
+                  if (col0 + j < p.rows) dstp[j] = __uint_as_float(v[j]);
+              }
+            }
+          }
+        }
+      } else {
+        // ---------------- the filter loop ----------------
+        // Per half-tile a thread's 64 columns arrive as one 64-register load (tcgen05.ld.32x32b.x64); the stage goes
+        // back to the MMA warp as soon as the load has landed, before anything is computed.  The two half-tiles of a
+        // tile use separate buffers so that the second load may be in flight while the first half is reduced (the
+        // register budget for this comes from setmaxnreg, see the role dispatch).
+        // Per half: four 16-column FMNMX3 trees -> four group maxima -> ONE compare and ONE (rarely taken) branch;
+        // a group whose maximum reaches the thread's threshold is not inspected, it is dumped into the thread's
+        // ring (5 stores).  Everything else that used to be decided per tile -- ring occupancy, the CTA-wide drain
+        // sequence, the bootstrap drain -- sits behind one warp-uniform branch that is only taken when some lane had
+        // a hit or the drain sequence moved.  (ncu, round 2: the nine branches per tile of the previous loop cost
+        // ~30 % of the epilogue's cycles in branch-resolution stalls.)
+        auto group_max = [](const uint32_t (&x)[64], int o) -> float {
+          const float m1 = max3(__uint_as_float(x[o + 0]), __uint_as_float(x[o + 1]), __uint_as_float(x[o + 2]));
+          const float m2 = max3(__uint_as_float(x[o + 3]), __uint_as_float(x[o + 4]), __uint_as_float(x[o + 5]));
+          const float m3 = max3(__uint_as_float(x[o + 6]), __uint_as_float(x[o + 7]), __uint_as_float(x[o + 8]));
+          const float m4 = max3(__uint_as_float(x[o + 9]), __uint_as_float(x[o + 10]), __uint_as_float(x[o + 11]));
+          const float m5 = max3(__uint_as_float(x[o + 12]), __uint_as_float(x[o + 13]), __uint_as_float(x[o + 14]));
+          return fmaxf(max3(m1, m2, m3), max3(m4, m5, __uint_as_float(x[o + 15])));
+        };
+        auto dump_half = [&](const uint32_t (&x)[64], const float (&g)[4], float t_eff, int gid0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (g[q] >= t_eff) {
               float4* rec = ring + cnt * (RING_REC_BYTES / 16);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                rec[j] = make_float4(__uint_as_float(x[g * 16 + 4 * j]), __uint_as_float(x[g * 16 + 4 * j + 1]),
-                                     __uint_as_float(x[g * 16 + 4 * j + 2]), __uint_as_float(x[g * 16 + 4 * j + 3]));
-              reinterpret_cast<int*>(rec + 4)[0] = gid0 + g * 16;
+                rec[j] = make_float4(__uint_as_float(x[q * 16 + 4 * j]), __uint_as_float(x[q * 16 + 4 * j + 1]),
+                                     __uint_as_float(x[q * 16 + 4 * j + 2]), __uint_as_float(x[q * 16 + 4 * j + 3]));
+              reinterpret_cast<int*>(rec + 4)[0] = gid0 + q * 16;
               ++cnt;
             }
           }
-        }
-      };
-
-      for (int n = sg.n0; n < sg.n1; ++n, ++t) {
-        // rows beyond B never produce candidates: their threshold is +inf.  The row's shared threshold is
-        // read (shared-space load, issued before the wait so that its latency hides behind it) once per tile.
-        float t_eff = live ? own_thr : INFINITY;
-        if (!kDense && live) {
+        };
+        if (!live) own_thr = INFINITY;   // rows beyond B never produce candidates
+        uint32_t va[64], vb[64];
+#pragma unroll 1
+        for (int n = sg.n0; n < sg.n1; ++n, ++t) {
+          // the row's shared threshold and the CTA's drain sequence: shared-space loads issued ahead of the waits.
+          // key_to_float(INT_MIN) is a NaN, which fmaxf ignores: an unset shared threshold leaves own_thr.
           const int kk = lds_volatile_s32(rowthr_s);
-          if (kk != INT_MIN) t_eff = fmaxf(own_thr, key_to_float(kk));
-        }
-        if (PROBE == 5) t_eff = INFINITY;
-        wait_tile();
-        if (PROBE == 1 || PROBE == 2 || PROBE == 4) {   // null epilogue
-          release_tile();
-          continue;
-        }
-        const uint32_t taddr = taddr_lane + static_cast<uint32_t>((t % ACC_STAGES) * BN);
-        const int col_gid0 = p.row_offset + n * BN + part * COLS;
+          const int seq0 = lds_volatile_s32(drain_seq_s);
+          float t_eff = fmaxf(own_thr, key_to_float(kk));
+          if (PROBE == 5) t_eff = INFINITY;
+          const int tile_gid0 = p.row_offset + n * BN;
 
-        if (kDense) {
-          uint32_t v[2][32];
-          tmem_ld_32x32(taddr, v[0]);
+          wait_half(t, 0);
+          tmem_ld_32x64(half_taddr(t, 0), va);
           tmem_ld_wait();
+          release_half(t, 0);
+          wait_half(t, 1);
+          tmem_ld_32x64(half_taddr(t, 1), vb);     // in flight while the first half is reduced
+          float ga[4];
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            if (c < CH - 1) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-            const int row = m_own * BM + r;
-            const int col0 = n * BN + part * COLS + c * 32;
-            if (row < p.B) {
-              float* dstp = p.dense_out + static_cast<size_t>(row) * p.dense_ld + col0;
-              if (col0 + 32 <= p.rows && (p.dense_ld & 3) == 0) {
+          for (int q = 0; q < 4; ++q) ga[q] = group_max(va, q * 16);
+          const bool hit_a = fmaxf(fmaxf(ga[0], ga[1]), fmaxf(ga[2], ga[3])) >= t_eff;
+          if (__builtin_expect(hit_a, 0)) dump_half(va, ga, t_eff, tile_gid0 + item_off(0));
+
+          tmem_ld_wait();
+          release_half(t, 1);
+          float gb[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  reinterpret_cast<float4*>(dstp)[j] =
-                      make_float4(__uint_as_float(v[c & 1][4 * j]), __uint_as_float(v[c & 1][4 * j + 1]),
-                                  __uint_as_float(v[c & 1][4 * j + 2]), __uint_as_float(v[c & 1][4 * j + 3]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.rows) dstp[j] = __uint_as_float(v[c & 1][j]);
+          for (int q = 0; q < 4; ++q) gb[q] = group_max(vb, q * 16);
+          const bool hit_b = fmaxf(fmaxf(gb[0], gb[1]), fmaxf(gb[2], gb[3])) >= t_eff;
+          if (__builtin_expect(hit_b, 0)) dump_half(vb, gb, t_eff, tile_gid0 + item_off(1));
+
+          if (__builtin_expect(__any_sync(0xffffffffu, hit_a || hit_b || boot || seq0 != drain_seen), 0)) {
+            // uniform point: a tile adds at most 8 records per thread, so draining whenever some lane
+            // holds more than RING_GROUPS-8 keeps every ring within capacity.  The first tile of a segment without
+            // a scout pass always drains (bootstrap): every stream then holds K entries and publishes its c-th best
+            // within the first microseconds, which defines the union bound.  Drains are synchronised across the
+            // CTA's epilogue warps: a warp that must drain bumps a shared sequence number and every warp drains at
+            // its next tile boundary.  A drain stalls the accumulator ring for everybody, so simultaneous
+            // drains cost one stall, not EW.
+            const bool need = __any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0));
+            int seq = lds_volatile_s32(drain_seq_s);
+            if (need && seq == drain_seen) {
+              if (lane == 0) {
+                atomicAdd(const_cast<int*>(&sSvc[3]), 1);
+                // a drain stalls the pair's accumulator ring: let the peer CTA drain at the same time
+                if (CG == 2 && p.pair_drain) red_add_cluster_u32(peer_drain_addr, 1u);
               }
+              seq += 1;
             }
-            if (c < CH - 1) tmem_ld_wait();
-          }
-          release_tile();
-          continue;
-        }
-
-        uint32_t v[2][32];
-        if (CH == 2) {
-          // 16 epilogue warps: this thread's 64 columns arrive with two loads issued together; the stage goes
-          // back to the MMA warp before anything is computed -- the other three warps of the SM sub-partition
-          // keep the TMEM read path busy meanwhile
-          tmem_ld_32x32(taddr, v[0]);
-          tmem_ld_32x32(taddr + 32, v[1]);
-          tmem_ld_wait();
-          release_tile();
-          filter_chunk(v[0], t_eff, col_gid0);
-          filter_chunk(v[1], t_eff, col_gid0 + 32);
-        } else {
-          // 8 epilogue warps: four loads, software pipelined one chunk ahead
-          tmem_ld_32x32(taddr, v[0]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            if (c < CH - 1) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-            filter_chunk(v[c & 1], t_eff, col_gid0 + c * 32);
-            if (c < CH - 1) tmem_ld_wait();
-            if (c == CH - 2) release_tile();   // all loads of this stage have landed: hand it back early
-          }
-        }
-        {
-          // uniform point, once per tile: a tile adds at most COLS/16 <= 8 records per thread, so draining
-          // whenever some lane holds more than RING_GROUPS-8 keeps every ring within capacity.
-          // The first tile of a segment always drains (bootstrap): every stream then holds K entries
-          // and publishes its c-th best within the first microseconds, which defines the union bound.
-          // Drains are synchronised across the CTA's epilogue warps: a warp that must drain bumps a
-          // shared sequence number and every warp drains at its next tile boundary.  A drain stalls the
-          // two-deep accumulator ring for everybody, so simultaneous drains cost one stall, not EW.
-          const bool need = __any_sync(0xffffffffu, cnt > RING_GROUPS - 8 || (boot && cnt > 0));
-          int seq = lds_volatile_s32(drain_seq_s);
-          if (need && seq == drain_seen) {
-            if (lane == 0) {
-              atomicAdd(const_cast<int*>(&sSvc[3]), 1);
-              // a drain stalls the pair's accumulator ring: let the peer CTA drain at the same time
-              if (CG == 2 && p.pair_drain) red_add_cluster_u32(peer_drain_addr, 1u);
+            if (need || seq != drain_seen) {
+              drain_seen = lds_volatile_s32(drain_seq_s);
+              boot = false;
+              drain();
             }
-            seq += 1;
-          }
-          if (need || seq != drain_seen) {
-            drain_seen = lds_volatile_s32(drain_seq_s);
-            boot = false;
-            drain();
           }
         }
       }
