@@ -368,22 +368,24 @@ def run_product(args, rank, world, local_rank):
             step_fn(x)
         barrier()
         model.profile_events = []
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         try:
             torch.cuda._sleep(int(1.9e6 * min(100.0, 10.0 + 1.5 * args.steps)))
         except Exception:
             pass
         ev[0].record()
-        for _ in range(args.steps):
+        for i in range(args.steps):
             o = step_fn(x)
-        ev[1].record()
+            ev[i + 1].record()
         barrier()
         sc = [a.elapsed_time(b) for a, b in model.profile_events]
         model.profile_events = None
-        t = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps, statistics.mean(sc) if sc else 0.0],
-                         dtype=torch.float64, device=device)
+        per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+        t = torch.tensor([ev[0].elapsed_time(ev[-1]) / args.steps, statistics.mean(sc) if sc else 0.0,
+                          statistics.median(per_step), max(per_step)], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed_variant.last_spread = {"ms_per_step_median": t[2].item(), "ms_per_step_max": t[3].item()}
         return t[0].item(), t[1].item(), {"ids": o["ids"].clone(), "scores": o["scores"].clone()}
 
     # ---- end-to-end through the public API with host buffers ----
@@ -446,7 +448,8 @@ def run_product(args, rank, world, local_rank):
         labels_strong = make_inputs(42)[1].to(device)
         strong_step = lambda x: retr.retrieve(x, k=TOPK, exclude_history=True, labels=labels_strong, ks=ks)
         ms_s, sc_s, last_strong = timed_variant(strong_step, ids_strong)
-        sub["strong"] = {"value": BATCH / (ms_s * 1e-3), "unit": "users/s", "ms_per_step": ms_s, "global_batch": BATCH,
+        sub["strong"] = {"value": BATCH / (ms_s * 1e-3), "unit": "users/s", "ms_per_step": ms_s, **timed_variant.last_spread,
+                         "kernel_ms": sc_s, "global_batch": BATCH,
                          "what": f"the same {BATCH} users on every rank against 1/{world} of the rows each "
                                  "(batch-sharded encoder, all-gather of the states and of the local lists)"}
     # trained models never have a zero bias (the reference's own init draws it from the truncated normal,
@@ -456,6 +459,7 @@ def run_product(args, rank, world, local_rank):
         model.model.bias.copy_(0.01 * torch.randn(N_ITEMS + 1, generator=g, device=device))
     ms_b, sc_b, last_bias = timed_variant(step, ids_dev)
     sub["bias"] = {"value": (BATCH * world if weak else BATCH) / (ms_b * 1e-3), "unit": "users/s", "ms_per_step": ms_b,
+                   **timed_variant.last_spread,
                    "kernel_ms": sc_b, "what": "the headline step with model.bias ~ N(0, 0.01) (folded-bias MMA active)"}
 
     # ---- parity of what was just timed (every rank checks users of ITS last step) ----
