@@ -346,6 +346,74 @@ LRB_DEVINL float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
   return m;
 }
+LRB_DEVINL float min3(float a, float b, float c) {
+  float m;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
+  return m;
+}
+
+// Log-depth reductions over small register arrays (3-input steps): the lock-step drain of the scoring kernel is a
+// chain of dependent instructions executed by one or two warps per SM sub-partition, so depth, not count, is its cost.
+template <int N>
+LRB_DEVINL float tree_max(const float (&v)[N]) {
+  if constexpr (N == 1) return v[0];
+  else if constexpr (N == 2) return fmaxf(v[0], v[1]);
+  else if constexpr (N == 3) return max3(v[0], v[1], v[2]);
+  else {
+    constexpr int M = (N + 2) / 3;
+    float t[M];
+#pragma unroll
+    for (int i = 0; i < N / 3; ++i) t[i] = max3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    if constexpr (N % 3 == 1) t[M - 1] = v[N - 1];
+    if constexpr (N % 3 == 2) t[M - 1] = fmaxf(v[N - 2], v[N - 1]);
+    return tree_max<M>(t);
+  }
+}
+template <int N>
+LRB_DEVINL float tree_min(const float (&v)[N]) {
+  if constexpr (N == 1) return v[0];
+  else if constexpr (N == 2) return fminf(v[0], v[1]);
+  else if constexpr (N == 3) return min3(v[0], v[1], v[2]);
+  else {
+    constexpr int M = (N + 2) / 3;
+    float t[M];
+#pragma unroll
+    for (int i = 0; i < N / 3; ++i) t[i] = min3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    if constexpr (N % 3 == 1) t[M - 1] = v[N - 1];
+    if constexpr (N % 3 == 2) t[M - 1] = fminf(v[N - 2], v[N - 1]);
+    return tree_min<M>(t);
+  }
+}
+template <int N>
+LRB_DEVINL int tree_min_int(const int (&v)[N]) {
+  if constexpr (N == 1) return v[0];
+  else if constexpr (N == 2) return min(v[0], v[1]);
+  else if constexpr (N == 3) return min(min(v[0], v[1]), v[2]);
+  else {
+    constexpr int M = (N + 2) / 3;
+    int t[M];
+#pragma unroll
+    for (int i = 0; i < N / 3; ++i) t[i] = min(min(v[3 * i], v[3 * i + 1]), v[3 * i + 2]);
+    if constexpr (N % 3 == 1) t[M - 1] = v[N - 1];
+    if constexpr (N % 3 == 2) t[M - 1] = min(v[N - 2], v[N - 1]);
+    return tree_min_int<M>(t);
+  }
+}
+template <int N>
+LRB_DEVINL int tree_sum_int(const int (&v)[N]) {
+  if constexpr (N == 1) return v[0];
+  else if constexpr (N == 2) return v[0] + v[1];
+  else if constexpr (N == 3) return v[0] + v[1] + v[2];
+  else {
+    constexpr int M = (N + 2) / 3;
+    int t[M];
+#pragma unroll
+    for (int i = 0; i < N / 3; ++i) t[i] = v[3 * i] + v[3 * i + 1] + v[3 * i + 2];
+    if constexpr (N % 3 == 1) t[M - 1] = v[N - 1];
+    if constexpr (N % 3 == 2) t[M - 1] = v[N - 2] + v[N - 1];
+    return tree_sum_int<M>(t);
+  }
+}
 
 // Explicit shared-space accessors (32-bit shared addresses).  The kernels carve dynamic shared
 // memory from an integer-aligned base, which makes nvcc fall back to generic LD/ST otherwise.

@@ -205,19 +205,21 @@ LRB_DEVINL float topk_consider_inl(float s, int gid, int row_limit_gid, float ow
   // rescan: worst = lowest score, ties broken towards the higher id.  All K score loads are issued
   // back to back (independent), the minimum and its position are found without branches; ids are
   // only consulted when the minimum is not unique (rare).
+  // (log-depth reductions: this runs in lock-step for the whole warp, its dependent-instruction depth is its cost)
   float v[KMAX];
 #pragma unroll
   for (int i = 0; i < KMAX; ++i) v[i] = i < K ? lds_f32(ls + i * ES) : INFINITY;
-  float m = v[0];
+  const float m = tree_min<KMAX>(v);
+  int pos[KMAX], one[KMAX];
 #pragma unroll
-  for (int i = 1; i < KMAX; ++i) m = fminf(m, v[i]);
-  int mp = 0, ties = 0;
-#pragma unroll
-  for (int i = KMAX - 1; i >= 0; --i) {
+  for (int i = 0; i < KMAX; ++i) {
     const bool eq = v[i] == m;
-    mp = eq ? i : mp;
-    ties += eq ? 1 : 0;
+    pos[i] = eq ? i : KMAX;
+    one[i] = eq ? 1 : 0;
   }
+  int mp = tree_min_int<KMAX>(pos);       // lowest position holding the minimum
+  const int ties = tree_sum_int<KMAX>(one);
+  if (mp >= KMAX) mp = 0;                 // (only if the minimum is a NaN, which never enters a set)
   if (ties > 1) {
     int mi = lds_s32(li + mp * ES);
     for (int i = mp + 1; i < K; ++i) {
@@ -249,7 +251,7 @@ __device__ __noinline__ float topk_consider(float s, int gid, int row_limit_gid,
 // and all lanes insert at the same time, so the insert cost is paid once per warp, not per lane.
 // -------------------------------------------------------------------------------------------
 #ifndef LRB_RING_GROUPS
-#define LRB_RING_GROUPS 16
+#define LRB_RING_GROUPS 24
 #endif
 constexpr int RING_GROUPS = LRB_RING_GROUPS;
 constexpr int RING_REC_BYTES = 80;   // 16 fp32 + int32 gid0, padded to a multiple of 16 B
@@ -317,14 +319,12 @@ __device__ __noinline__ float compact_ring(const float4* ring, int cnt, float ow
     s[8] = cur.c.x; s[9] = cur.c.y; s[10] = cur.c.z; s[11] = cur.c.w;
     s[12] = cur.d.x; s[13] = cur.d.y; s[14] = cur.d.z; s[15] = cur.d.w;
     while (true) {
-      float best = -INFINITY;
-      int bj = 0;
+      // best remaining score of the record and its lowest column (lower id wins ties); NaNs never win
+      const float best = tree_max<16>(s);
+      int col[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const bool gt = s[j] > best;   // strict: the lowest column wins ties (lower id first)
-        best = gt ? s[j] : best;
-        bj = gt ? j : bj;
-      }
+      for (int j = 0; j < 16; ++j) col[j] = (s[j] == best) ? j : 16;
+      const int bj = tree_min_int<16>(col) & 15;
       const bool pass = act && best > -INFINITY && best >= fmaxf(own_thr, shared_thr);
       if (!__any_sync(0xffffffffu, pass)) break;
       if (pass) {
