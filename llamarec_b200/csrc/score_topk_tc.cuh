@@ -17,7 +17,8 @@
 // issues M = 256 MMAs, both CTAs read their own 128-lane accumulators out of their own TMEM.
 // Warp roles (384 threads): warp 0 = TMA producer, warps 1-2 = MMA issuers (leader CTA only; even / odd tiles),
 // warp 2 also allocates TMEM, warp 3 = builds the "ones" block, then threshold service (union bound),
-// warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4).., 64 of the 128 columns of every half-tile).  The
+// warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4).. of ONE half-tile per tile: warps 4-7 the first, warps
+// 8-11 the second).  The
 // producer / MMA / service warpgroup gives registers to the epilogue warpgroups (setmaxnreg 56 / 224).  The bias is
 // folded into the GEMM as a fifth K=16 MMA per half-tile.  Consecutive launches of one call (user chunks) overlap via
 // programmatic dependent launch.
@@ -49,6 +50,14 @@ constexpr int DONE_RING = 8;                // tiles in the ring of "half-tile c
 // cycles per tile) but lose in the kernel (96 registers per thread, twice the per-thread candidate sets): 5.86 vs 5.25 ms.
 #ifndef LRB_EW20
 #define LRB_EW20 8
+#endif
+// LRB_OWN_HALF = 1 (default): the two column parts of the epilogue do not split every half-tile's columns (64 + 64)
+// but take one half-tile each (part p reads all 128 columns of half-tile p): a stage is then released by 4 warps per
+// CTA instead of 8, every warp waits / releases once per tile instead of twice, and the two warps of an SM
+// sub-partition use its TMEM read path at different times.  Same-box A/B on B200 (tools/tc_check, product build):
+// 4.76-4.91 -> 4.46-4.58 ms at 4096 x 10M, 5.07-5.31 -> 4.90-4.97 with bias + exclusion, 5.16-5.22 -> 4.95 at 32768 x 1.25M.
+#ifndef LRB_OWN_HALF
+#define LRB_OWN_HALF 1
 #endif
 constexpr int SLOT_PARTS = LRB_EW20 / 4;
 // harness timeline (PROBE builds): clock stamps of CTA 0 for tiles [TL_T0, TL_T0 + TL_N), 24 slots per tile behind the
@@ -503,7 +512,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NS; ++i) mbar_init(&full_bar[i], 1);
     for (int i = 0; i < 2 * DONE_RING; ++i) mbar_init(&done_bar[i], 1);
-    for (int i = 0; i < ACC_STAGES; ++i) mbar_init(&tmem_empty_bar[i], EW * CG);   // pair: both CTAs' epilogues arrive on the leader's
+    for (int i = 0; i < ACC_STAGES; ++i) mbar_init(&tmem_empty_bar[i], (LRB_OWN_HALF ? EW / 2 : EW) * CG);   // pair: both CTAs' epilogues arrive on the leader's
     mbar_init(a_full_bar, 1);
     mbar_init(a_empty_bar, 2);   // one commit from each MMA-issuing warp
     mbar_fence_init();
@@ -749,10 +758,19 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // of the 256-item tile, i.e. this warp's columns are 64 consecutive items starting at item_off(h).
     constexpr int HCOLS = HN / PARTS;   // 64
     static_assert(HCOLS == 64, "one tcgen05.ld.32x32b.x64 per warp and half-tile");
-    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(part * HCOLS);
-    auto half_taddr = [&](int tt, int h) { return taddr_lane + static_cast<uint32_t>(((tt & 1) * 2 + h) * HN); };
-    auto item_off = [&](int h) { return CG == 2 ? part * 128 + h * 64 : h * 128 + part * 64; };
-    auto wait_half = [&](int tt, int h) {   // the accumulator of half-tile h of tile tt is complete
+    // A warp's work per tile = two 64-column BLOCKS q = 0, 1.  Shared half-tiles (LRB_OWN_HALF == 0): block q is this
+    // warp's column part of half-tile q.  Own half-tiles: both blocks are the two column halves of half-tile `part`.
+    constexpr bool kOwn = LRB_OWN_HALF != 0;
+    const uint32_t taddr_quad = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    auto half_taddr = [&](int tt, int q) {
+      const int h = kOwn ? part : q, cb = kOwn ? q : part;
+      return taddr_quad + static_cast<uint32_t>(((tt & 1) * 2 + h) * HN + cb * HCOLS);
+    };
+    auto item_off = [&](int q) {
+      const int h = kOwn ? part : q, cb = kOwn ? q : part;
+      return CG == 2 ? cb * 128 + h * 64 : h * 128 + cb * 64;
+    };
+    auto wait_half_raw = [&](int tt, int h) {   // the accumulator of half-tile h of tile tt is complete
       uint64_t* bar = &done_bar[(tt % DONE_RING) * 2 + h];
       if (PROBE != 0) {
         const long long w0 = clock64();
@@ -765,7 +783,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       tc_fence_after();
     };
-    auto release_half = [&](int tt, int h) {   // this warp's loads of that accumulator stage have landed in its registers
+    auto release_half_raw = [&](int tt, int h) {   // this warp's loads of that accumulator stage have landed in its registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {            // (consecutive mbarriers are 8 bytes apart, in either address window)
@@ -775,6 +793,15 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (PROBE != 0 && h == 1 && blockIdx.x == 0 && p.probe_out != nullptr && tt >= TL_T0 && tt < TL_T0 + TL_N)
           p.probe_out[TL_BASE + (tt - TL_T0) * 24 + 10 + ew] = clock64();
       }
+    };
+    // block-level wrappers: with own half-tiles a warp waits before its first block and releases after its second
+    auto wait_half = [&](int tt, int q) {
+      if (!kOwn) wait_half_raw(tt, q);
+      else if (q == 0) wait_half_raw(tt, part);
+    };
+    auto release_half = [&](int tt, int q) {
+      if (!kOwn) release_half_raw(tt, q);
+      else if (q == 1) release_half_raw(tt, part);
     };
     while (walk.next(sg)) {
       ++seg_idx;
@@ -1012,10 +1039,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
           wait_half(t, 0);
           tmem_ld_32x64(half_taddr(t, 0), va);
-          tmem_ld_wait();
-          release_half(t, 0);
-          wait_half(t, 1);
-          tmem_ld_32x64(half_taddr(t, 1), vb);     // in flight while the first half is reduced
+          if (!kOwn) {
+            tmem_ld_wait();
+            release_half(t, 0);
+            wait_half(t, 1);
+          }
+          tmem_ld_32x64(half_taddr(t, 1), vb);     // in flight while the first block is reduced
           float ga[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) ga[q] = group_max(va, q * 16);
