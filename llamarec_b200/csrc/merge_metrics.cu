@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
     // floor for the global-memory path: entries must be strictly "after" the previous winner
     float prev_s = INFINITY;
     int prev_id = -1;
+    // the merged list is collected in registers (lane k % 32 holds entry k) and written once at the end: two
+    // coalesced stores per user instead of 2 * K_out four-byte stores by lane 0 -- in scatter mode those are remote
+    // stores over NVLink (8-GPU step: 132 us for 32768 users before this change)
+    float res_s[2] = {-INFINITY, -INFINITY};
+    int res_i[2] = {-1, -1};
     for (int k = 0; k < p.K_out; ++k) {
       float w_s;
       int w_id;
@@ -171,12 +176,18 @@ __global__ void __launch_bounds__(WARPS * 32) merge_metrics_kernel(const Params 
       prev_s = w_s;
       prev_id = w_id;
       const bool valid = w_id != INT_MAX;
-      if (lane == 0) {
+      if (lane == (k & 31)) {
+        if (k < 32) { res_s[0] = valid ? w_s : -INFINITY; res_i[0] = valid ? w_id : -1; }
+        else if (k < 64) { res_s[1] = valid ? w_s : -INFINITY; res_i[1] = valid ? w_id : -1; }
+      }
+      if (k >= 64 && lane == 0) {   // (lists longer than 64 entries: not used by any caller, kept correct)
         out_s[k] = valid ? w_s : -INFINITY;
         out_i[k] = valid ? w_id : -1;
       }
       if (valid && my_rank < 0 && static_cast<long long>(w_id) == label) my_rank = k;
     }
+    if (lane < p.K_out) { out_s[lane] = res_s[0]; out_i[lane] = res_i[0]; }
+    if (lane + 32 < p.K_out) { out_s[lane + 32] = res_s[1]; out_i[lane + 32] = res_i[1]; }
     if (p.label_rank && lane == 0) p.label_rank[b] = my_rank;
     if (p.labels && my_rank >= 0 && lane == 0) {
       // one relevant item per user: Recall@k = [r<k], MRR@k = [r<k]/(r+1), NDCG@k = [r<k]/log2(r+2)
