@@ -297,6 +297,37 @@ __global__ void __launch_bounds__(128) lru_scan_kernel(const ScanParams p) {
   // written back.  With a mean of ~9 real tokens per user the kernel is latency-bound, not bandwidth-bound: one
   // chunk puts SCAN_CHUNK rows in flight per thread instead of the single prefetched row of the first version.
   float2* row = p.bu + static_cast<size_t>(base) * LRB_H + c;
+
+  // Fast path: a LEFT-PADDED row (no padding after a real item -- what the reference's dataloaders produce,
+  // dataloader/lru.py:98-118,129-180).  The tree scan then equals  h_p = lambda * (mask_{p-1} h_{p-1}) + bu_p
+  // (SURVEY probe P1): 4 FMAs per step instead of the ~150 instructions of the general carry set below, which
+  // made this kernel instruction-bound (ncu round 2: issue active 71 %, 157 warp instructions per warp and step).
+  bool monotone = true;
+  for (int t = first + 1 + c; t < p.L; t += 128) monotone = monotone && !(s_mask[t - 1] != 0 && s_mask[t] == 0);
+  if (__syncthreads_and(monotone ? 1 : 0)) {
+    float hr = 0.f, hi = 0.f;   // mask_{p-1} * h_{p-1}
+    for (int j0 = 0; j0 < n; j0 += SCAN_CHUNK) {
+      float2 v[SCAN_CHUNK];
+#pragma unroll
+      for (int u = 0; u < SCAN_CHUNK; ++u)
+        v[u] = (j0 + u < n) ? row[static_cast<size_t>(j0 + u) * LRB_H] : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < SCAN_CHUNK; ++u) {
+        const int j = j0 + u;
+        if (j < n) {
+          const float nr = v[u].x + (hr * lr - hi * li);
+          const float ni = v[u].y + (hr * li + hi * lr);
+          if (!p.last_only) row[static_cast<size_t>(j) * LRB_H] = make_float2(nr, ni);
+          else if (j == n - 1) p.h_last[static_cast<size_t>(b) * LRB_H + c] = make_float2(nr, ni);
+          const bool m = s_mask[first + j] != 0;
+          hr = m ? nr : 0.f;
+          hi = m ? ni : 0.f;
+        }
+      }
+    }
+    return;
+  }
+
   for (int j0 = 0; j0 < n; j0 += SCAN_CHUNK) {
     float2 v[SCAN_CHUNK];
 #pragma unroll
