@@ -71,8 +71,10 @@ LRB_DEVINL void mbar_arrive(uint64_t* bar) {
 // instead of returning after a few tens of cycles: a spinning try_wait + branch pair takes issue slots from the other
 // warps of its SM sub-partition (scoring kernel, ncu round 2: 10 % of all issued instructions were such spins, and
 // the epilogue warps that share a sub-partition with an MMA-issuing warp ran ~300 cycles per tile behind the others).
+// (Same-box A/B on B200: the hint does not change the kernel's time either way; 20 us keeps a waiter parked for
+// most of a hand-off and bounds what a missed wake-up could cost.)
 #ifndef LRB_MBAR_SUSPEND_HINT
-#define LRB_MBAR_SUSPEND_HINT 0x989680u
+#define LRB_MBAR_SUSPEND_HINT 20000u
 #endif
 LRB_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
