@@ -385,7 +385,8 @@ def run_product(args, rank, world, local_rank):
                           statistics.median(per_step), max(per_step)], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        timed_variant.last_spread = {"ms_per_step_median": t[2].item(), "ms_per_step_max": t[3].item()}
+        timed_variant.last_spread = {"ms_per_step_median": t[2].item(), "ms_per_step_max": t[3].item(),
+                                     "steps_ms_this_rank": [round(v, 3) for v in per_step]}
         return t[0].item(), t[1].item(), {"ids": o["ids"].clone(), "scores": o["scores"].clone()}
 
     # ---- end-to-end through the public API with host buffers ----
