@@ -341,9 +341,10 @@ static void time_topk(int B, int rows, int K, bool with_bias, bool with_excl) {
       for (int i = 0; i < 16; ++i) {
         printf("   t+%2d %6lld %6lld (ops %6lld stage %6lld) |", i, tl[i * 24] - base, tl[i * 24 + 1] - base, tl[i * 24 + 18] - base,
                tl[i * 24 + 19] - base);
-        for (int w = 0; w < 8; ++w) printf(" %6lld", tl[i * 24 + 2 + w] - base);
+        // (a warp stamps only the half-tile it owns: warps 0-3 see the first half-tile "done", warps 4-7 release the second)
+        for (int w = 0; w < 8; ++w) { if (tl[i * 24 + 2 + w]) printf(" %6lld", tl[i * 24 + 2 + w] - base); else printf("      -"); }
         printf(" |");
-        for (int w = 0; w < 8; ++w) printf(" %6lld", tl[i * 24 + 10 + w] - base);
+        for (int w = 0; w < 8; ++w) { if (tl[i * 24 + 10 + w]) printf(" %6lld", tl[i * 24 + 10 + w] - base); else printf("      -"); }
         printf("\n");
       }
     }
