@@ -113,13 +113,18 @@ int lrb_encode_fwd(const void* ids, int id_bytes, int B, int L, const float* tab
  * reduces them (and, after an all-gather, the lists of other ranks) to the final top-K.
  *   precision 0 (bf16): u_bf16 [B][64] bf16, table_bf16 [rows][64] bf16 -- tcgen05 tensor cores
  *   precision 1 (fp32): u_f32  [B][64] fp32, table_f32  [rows][64] fp32 -- exact FFMA path for
- *                       small catalogues (bit-comparable with the fp32 reference)
+ *                       small catalogues (bit-comparable with the fp32 reference).  While a block of
+ *                       >= 128 users' score rows fits in the scratch buffer (rows <= ~560 k) the scores are
+ *                       written out once and one warp per user applies the history mask and selects the
+ *                       top K with a radix select -- literally scores[b, history] = -inf; torch.topk
+ *                       (trainer/lru.py:36-38,82-84) -- and ONE sorted list per user comes out (slots == 1);
+ *                       beyond that a streaming kernel emits one partial list per item-range split
  *   bias_pad / bias_blk: from lrb_prepare_table (fp32 path reads bias_pad; bf16 path reads bias_blk,
  *   NULL = zero bias).  row_offset: global id of local row 0 (row sharding).
  *   excl_sorted/excl_bloom/excl_stride: from lrb_prepare_sequences, NULL = no exclusion
  *   (BaseTrainer.validate calls calculate_metrics(exclude_history=False), trainer/base.py:141).
  * Outputs (caller allocated): part_scores/part_ids [B][slots][K], part_cnt [B][slots];
- *   scratch: lrb_score_scratch_bytes(B).
+ *   scratch: lrb_score_scratch_bytes(B) (both precisions).
  * ------------------------------------------------------------------------------------------ */
 int lrb_score_topk_slots(int B, int64_t rows, int precision, int* slots);
 size_t lrb_score_scratch_bytes(int B);

@@ -20,8 +20,10 @@ namespace lrb {
 namespace mm {
 
 constexpr int WARPS = 8;
-constexpr int MAX_PER_LANE = 16;   // register-resident entries per lane (up to 512 per user); the kernel is
-                                   // instantiated for 2/4/8/16 so that narrow fan-in does not pay for 16
+constexpr int MAX_PER_LANE = 32;   // register-resident entries per lane (up to 1024 per user); the kernel is
+                                   // instantiated for 2/4/8/16/32 so that narrow fan-in does not pay for 32.
+                                   // (Beyond that every round re-reads the lists from global memory: the 19 x 50
+                                   // candidates per user of the exact-fp32 path at C3 took 494 us that way.)
 constexpr int MAX_KS = 8;
 constexpr int MAX_DST = 16;    // scatter mode: destination buffers (ranks of one node)
 
@@ -268,6 +270,7 @@ int merge_launch(const float* list_scores, const int32_t* list_ids, const int32_
   if (total <= 64) mm::merge_metrics_kernel<2><<<grid, mm::WARPS * 32, 0, st>>>(p);
   else if (total <= 128) mm::merge_metrics_kernel<4><<<grid, mm::WARPS * 32, 0, st>>>(p);
   else if (total <= 256) mm::merge_metrics_kernel<8><<<grid, mm::WARPS * 32, 0, st>>>(p);
+  else if (total <= 512) mm::merge_metrics_kernel<16><<<grid, mm::WARPS * 32, 0, st>>>(p);
   else mm::merge_metrics_kernel<mm::MAX_PER_LANE><<<grid, mm::WARPS * 32, 0, st>>>(p);
   LRB_CUDA_TRY(cudaGetLastError());
   return LRB_OK;

@@ -181,6 +181,198 @@ inline int splits_for(int B, long long rows, int sms) {
   return static_cast<int>(want);
 }
 
+// --------------------------------------------------------------------------------------------
+// Small catalogues: dense scores + per-user selection.
+//
+// The streaming kernel above keeps one top-K set per thread and pays a lock-step insertion for almost
+// every item while a thread has seen fewer than ~32 K items (B200, C3 = 2048 users x 11001 items, K = 50:
+// 875 us, of which the contraction itself is < 10 %, and 494 us more to merge 19 x 50 candidates per user).
+// When a block of users' score rows fits in the scratch buffer the scores are written out once instead
+// (score_f32_kernel<true>, same fp32 summation order) and ONE WARP PER USER selects the top K from its row:
+//   1. the history mask as the reference applies it -- scores[b, history] = -inf (trainer/lru.py:36-38),
+//   2. a 4-pass radix select (8 bits per pass, per-warp shared-memory histogram) for the K-th largest key,
+//   3. one more pass collecting everything above the K-th key plus the lowest-id entries equal to it,
+//   4. a rank sort of the <= K survivors into (score desc, id asc) order.
+// The output is ONE sorted list per user (slots == 1), in the part_* layout the merge kernel consumes.
+// --------------------------------------------------------------------------------------------
+constexpr int SEL_WARPS = 8;
+
+struct SelParams {
+  float* dense;          // [nb][ld] scores of this user block (scratch; the history mask is written into it)
+  long long ld;
+  int nb;                // users in the block
+  int b0;                // global index of the block's first user
+  int rows, row_offset, K;
+  const int* excl_sorted;
+  int excl_stride;
+  float* part_scores;    // [B][K]
+  int* part_ids;
+  int* part_cnt;         // [B]
+};
+
+LRB_DEVINL unsigned sel_key(float v) {   // order-preserving unsigned key; NaN sorts below everything
+  return (v == v) ? (static_cast<unsigned>(float_to_key(v)) ^ 0x80000000u) : 0u;
+}
+
+__global__ void __launch_bounds__(SEL_WARPS * 32) select_topk_kernel(const SelParams p) {
+  __shared__ unsigned s_hist[SEL_WARPS][4 * 256];
+  __shared__ float s_sc[SEL_WARPS][64];
+  __shared__ int s_id[SEL_WARPS][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bl = blockIdx.x * SEL_WARPS + warp;
+  if (bl >= p.nb) return;                       // (no block-level barrier below)
+  const int b = p.b0 + bl;
+  float* row = p.dense + static_cast<size_t>(bl) * p.ld;
+  const int rows = p.rows;
+  unsigned* hist = s_hist[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // 1. history mask
+  if (p.excl_sorted != nullptr) {
+    const int* ex = p.excl_sorted + static_cast<size_t>(b) * p.excl_stride;
+    for (int j = lane; j < p.excl_stride; j += 32) {
+      const int id = ex[j];
+      const long long col = static_cast<long long>(id) - p.row_offset;
+      if (id != INT_MAX && col >= 0 && col < rows) row[col] = -INFINITY;
+    }
+  }
+  __syncwarp();
+
+  // 2. radix select: the `need`-th largest key among the row's entries
+  const int K_eff = p.K < rows ? p.K : rows;
+  unsigned prefix = 0u;
+  int need = K_eff;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const unsigned hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) hist[lane + 32 * j] = 0u;
+    __syncwarp();
+    // Four row entries per lane and iteration are loaded before any is counted (the loop is latency-bound: one
+    // warp per user, ~14 resident warps per SM at C3), and the histogram exists in four copies selected by lane % 4:
+    // scores share their sign and exponent bits, so in the first passes nearly every lane hits the same bin and
+    // the shared-memory atomics serialise.  (Grouping the lanes with match.any instead was twice as slow.)
+    unsigned* my_hist = hist + (lane & 3) * 256;
+    for (int base = lane; base < rows; base += 128) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = (base + 32 * q < rows) ? row[base + 32 * q] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned key = sel_key(v[q]);
+        if (base + 32 * q < rows && (key & hi_mask) == prefix) atomicAdd(&my_hist[(key >> shift) & 255u], 1u);
+      }
+    }
+    __syncwarp();
+    // lane l owns bins [8l, 8l+8); `above` = entries in bins owned by higher lanes
+    unsigned own[8];
+    unsigned mine = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int bi = lane * 8 + j;
+      own[j] = hist[bi] + hist[256 + bi] + hist[512 + bi] + hist[768 + bi];
+      mine += own[j];
+    }
+    unsigned incl = mine;                       // inclusive suffix sum over lanes (high lanes first)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += v;
+    }
+    const unsigned above = incl - mine;
+    const bool holder = above < static_cast<unsigned>(need) && static_cast<unsigned>(need) <= incl;
+    int bin = 0;
+    unsigned above_bin = 0u;
+    if (holder) {
+      unsigned acc = above;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (acc < static_cast<unsigned>(need) && static_cast<unsigned>(need) <= acc + own[j]) { bin = lane * 8 + j; above_bin = acc; }
+        acc += own[j];
+      }
+    }
+    const unsigned hb = __ballot_sync(0xffffffffu, holder);
+    const int src = __ffs(hb) - 1;              // exactly one holder (need >= 1 and need <= matching entries)
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    above_bin = __shfl_sync(0xffffffffu, above_bin, src);
+    prefix |= static_cast<unsigned>(bin) << shift;
+    need -= static_cast<int>(above_bin);
+    __syncwarp();
+  }
+  // prefix = key of the K-th largest entry; `need` entries equal to it are wanted (lowest columns first)
+  const int n_gt_total = K_eff - need;
+
+  // 3. collect (ballot prefix sums keep the equal-key entries in column order)
+  int n_gt = 0, n_eq = 0;
+  for (int base = 0; base < rows; base += 128) {
+    float vv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) vv[q] = (base + 32 * q + lane < rows) ? row[base + 32 * q + lane] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = base + 32 * q + lane;
+      const bool valid = c < rows;
+      const float v = vv[q];
+      const unsigned key = valid ? sel_key(v) : 0u;
+      const bool gt = valid && key > prefix;
+      const bool eq = valid && key == prefix;
+      const unsigned bg = __ballot_sync(0xffffffffu, gt);
+      const unsigned be = __ballot_sync(0xffffffffu, eq);
+      if (gt) {
+        const int idx = n_gt + __popc(bg & lt_mask);
+        s_sc[warp][idx] = v;
+        s_id[warp][idx] = c + p.row_offset;
+      }
+      if (eq) {
+        const int r = n_eq + __popc(be & lt_mask);
+        if (r < need) {
+          s_sc[warp][n_gt_total + r] = v;
+          s_id[warp][n_gt_total + r] = c + p.row_offset;
+        }
+      }
+      n_gt += __popc(bg);
+      n_eq += __popc(be);
+    }
+    if (n_gt >= n_gt_total && n_eq >= need) break;   // warp-uniform
+  }
+  __syncwarp();
+
+  // 4. rank sort into (score desc, id asc); -inf (masked / padding) and NaN entries are not emitted
+  int n_valid = 0;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int e = lane + 32 * q;
+    bool ok = false;
+    int rank = 0;
+    float sc = 0.f;
+    int id = 0;
+    if (e < K_eff) {
+      sc = s_sc[warp][e];
+      id = s_id[warp][e];
+      ok = sc > -INFINITY;
+      for (int j = 0; j < K_eff; ++j) {
+        const float sj = s_sc[warp][j];
+        const int ij = s_id[warp][j];
+        rank += (sj > -INFINITY && better(sj, ij, sc, id)) ? 1 : 0;
+      }
+    }
+    if (ok) {
+      p.part_scores[static_cast<size_t>(b) * p.K + rank] = sc;
+      p.part_ids[static_cast<size_t>(b) * p.K + rank] = id;
+    }
+    n_valid += __popc(__ballot_sync(0xffffffffu, ok));
+  }
+  if (lane == 0) p.part_cnt[b] = n_valid;
+}
+
+// users whose score rows fit in `bytes` of scratch (multiple of 128, the dense kernel's user tile), 0 = none
+inline long long select_block_users(long long rows, size_t bytes) {
+  const long long ld = (rows + 3) / 4 * 4;
+  const long long u = static_cast<long long>(bytes / (static_cast<size_t>(ld) * 4));
+  return u / ROWS * ROWS;
+}
+
 }  // namespace f32
 
 // ============================================================================================
@@ -389,6 +581,11 @@ static long long* const g_debug_probe_out = nullptr;
 
 extern "C" {
 
+static size_t ring_bytes();
+// users per block of the exact-fp32 "dense + select" path (0 = the catalogue is too large for it): what fits in
+// the candidate-ring part of the scratch buffer, which lrb_score_scratch_bytes() reserves for every B
+static long long f32_select_users(long long rows) { return lrb::f32::select_block_users(rows, 2 * ring_bytes()); }
+
 int lrb_score_topk_slots(int B, int64_t rows, int precision, int* slots) {
   LRB_REQUIRE(B > 0 && rows > 0 && slots != nullptr, "lrb_score_topk_slots: bad arguments");
   int sms = lrb::device_sm_count();
@@ -396,7 +593,8 @@ int lrb_score_topk_slots(int B, int64_t rows, int precision, int* slots) {
   if (precision == 0) {
     *slots = lrb::chunked_slots(B, rows, sms);
   } else if (precision == 1) {
-    *slots = lrb::f32::splits_for(B, rows, sms);
+    // small catalogues: dense scores + per-user selection -> one sorted list per user
+    *slots = f32_select_users(rows) > 0 ? 1 : lrb::f32::splits_for(B, rows, sms);
   } else {
     return lrb::set_error(LRB_ERR_BAD_ARG, "precision must be 0 (bf16) or 1 (fp32)");
   }
@@ -456,6 +654,39 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
   LRB_REQUIRE((excl_sorted == nullptr) == (excl_bloom == nullptr), "lrb_score_topk: exclusion list and bloom filter must come together");
   cudaStream_t st = as_stream(stream);
   int sms = device_sm_count();
+  if (precision == 1 && f32_select_users(rows) > 0) {
+    LRB_REQUIRE(slots == 1, "lrb_score_topk: slots=%d but lrb_score_topk_slots says 1", slots);
+    LRB_REQUIRE(scratch != nullptr, "lrb_score_topk: scratch is required");
+    const long long blk = f32_select_users(rows);
+    const long long ld = (rows + 3) / 4 * 4;
+    float* dense = static_cast<float*>(scratch);
+    const size_t smem = (f32::IT * f32::D + f32::IT) * 4 + static_cast<size_t>(f32::ROWS) * (f32::IT + 1) * 4;
+    auto dkern = f32::score_f32_kernel<true>;
+    LRB_CUDA_TRY(cudaFuncSetAttribute(dkern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    for (long long b0 = 0; b0 < B; b0 += blk) {
+      const int nb = static_cast<int>(B - b0 < blk ? B - b0 : blk);
+      f32::Params p;
+      p.u = static_cast<const float*>(u) + b0 * f32::D;
+      p.table = static_cast<const float*>(table);
+      p.bias_pad = bias_pad;
+      p.B = nb; p.rows = static_cast<int>(rows); p.row_offset = 0; p.K = 0;
+      p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
+      p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
+      p.dense_out = dense; p.dense_ld = ld;
+      const int splits = f32::splits_for(nb, rows, sms);
+      dim3 grid(static_cast<unsigned>((nb + f32::ROWS - 1) / f32::ROWS), splits);
+      dkern<<<grid, f32::ROWS, smem, st>>>(p);
+      LRB_CUDA_TRY(cudaGetLastError());
+      f32::SelParams sp;
+      sp.dense = dense; sp.ld = ld; sp.nb = nb; sp.b0 = static_cast<int>(b0);
+      sp.rows = static_cast<int>(rows); sp.row_offset = static_cast<int>(row_offset); sp.K = K;
+      sp.excl_sorted = excl_sorted; sp.excl_stride = excl_stride;
+      sp.part_scores = part_scores; sp.part_ids = part_ids; sp.part_cnt = part_cnt;
+      f32::select_topk_kernel<<<(nb + f32::SEL_WARPS - 1) / f32::SEL_WARPS, f32::SEL_WARPS * 32, 0, st>>>(sp);
+      LRB_CUDA_TRY(cudaGetLastError());
+    }
+    return LRB_OK;
+  }
   if (precision == 1) {
     const int splits = f32::splits_for(B, rows, sms);
     LRB_REQUIRE(slots == splits, "lrb_score_topk: slots=%d but lrb_score_topk_slots says %d", slots, splits);

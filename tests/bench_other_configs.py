@@ -60,9 +60,21 @@ out["c2_beauty_B64"] = {"forward_all_positions_ms": t_fwd * 1e3, "forward_users_
 # train-step forward loss (trainer/lru.py:20-28) without the logits tensor, against the oracle's full-logits CE
 lab = torch.zeros_like(ids[:64]); lab[:, :-1] = ids[:64, 1:]; lab[:, -1] = labels[:64].view(-1); lab[ids[:64] == 0] = 0
 yl = lab.to(dev)
-t_ce = gpu_time(lambda: m.ce_loss(x, yl))
+def fwd_loss(mm, xx, yy):
+    with torch.no_grad():                  # value only (lrb_ce_loss_fwd); with autograd enabled ce_loss is the train step
+        return mm.ce_loss(xx, yy)
+
+
+def train_step(mm, xx, yy):                # loss + the gradient of every parameter (lrb_train_step) through autograd
+    mm.zero_grad(set_to_none=True)
+    mm.ce_loss(xx, yy).backward()
+
+
+t_ce = gpu_time(lambda: fwd_loss(m, x, yl))
+t_ts = gpu_time(lambda: train_step(m, x, yl), n=10)
 t0 = time.perf_counter(); ref_loss = O.ce_loss(ids[:64], lab, sd).item(); tcl = time.perf_counter() - t0
-out["c2_beauty_B64"].update({"ce_loss_fwd_ms": t_ce * 1e3, "ce_loss": m.ce_loss(x, yl).item(), "cpu_oracle_ce_loss": ref_loss,
+out["c2_beauty_B64"].update({"ce_loss_fwd_ms": t_ce * 1e3, "train_step_fwd_bwd_ms": t_ts * 1e3,
+                             "ce_loss": fwd_loss(m, x, yl).item(), "cpu_oracle_ce_loss": ref_loss,
                              "cpu_oracle_ce_loss_ms": tcl * 1e3})
 xb = ids.to(dev)
 t_big = gpu_time(lambda: m.retrieve(xb, k=20), n=10)
@@ -79,8 +91,10 @@ t16 = gpu_time(lambda: m.retrieve(x, k=50, labels=y, ks=list(cfg.metric_ks), pre
 t0 = time.perf_counter(); s = O.mask_history(O.last_scores(ids, sd), ids); MO.recall_mrr_ndcg(s, labels, cfg.metric_ks); tc = time.perf_counter() - t0
 lab = torch.zeros_like(ids); lab[:, :-1] = ids[:, 1:]; lab[:, -1] = labels.view(-1); lab[ids == 0] = 0
 yl = lab.to(dev)
-t_ce3 = gpu_time(lambda: m.ce_loss(x, yl), n=10)
-out["c3_games_B2048_train_step_loss"] = {"ce_loss_fwd_ms": t_ce3 * 1e3, "ce_loss": m.ce_loss(x, yl).item(),
+t_ce3 = gpu_time(lambda: fwd_loss(m, x, yl), n=10)
+t_ts3 = gpu_time(lambda: train_step(m, x, yl), n=5, warm=2)
+out["c3_games_B2048_train_step_loss"] = {"ce_loss_fwd_ms": t_ce3 * 1e3, "train_step_fwd_bwd_ms": t_ts3 * 1e3,
+                                         "ce_loss": fwd_loss(m, x, yl).item(),
                                          "logits_bytes_never_materialised": 2048 * 50 * (cfg.num_items + 1) * 4}
 out["c3_games_B2048"] = {"calculate_metrics_fp32_ms": t32 * 1e3, "fp32_users_per_s": 2048 / t32,
                          "bf16_k50_ms": t16 * 1e3, "bf16_users_per_s": 2048 / t16, "cpu_oracle_users_per_s": 2048 / tc}
