@@ -568,6 +568,48 @@ def test_k_larger_than_valid_items_and_no_exclusion():
     assert_topk_equivalent(res["ids"].cpu().numpy(), res["scores"].cpu().numpy(), ref_i.numpy(), ref_s.numpy())
 
 
+def test_exact_fp32_selection_with_massive_ties_and_row_shards():
+    """The exact-fp32 path of small catalogues (dense scores + one warp per user: history mask, radix select, rank
+    sort) on a table whose rows repeat every 7 items and whose bias is zero: every score occurs ~n/7 times, so the
+    K-th key is tied many times over and the list is decided by the tie rule alone -- (score desc, id asc), i.e. the
+    lowest ids of each tied class, after the history mask.  Also as two row shards merged (virtual ranks), K = 50,
+    and a catalogue whose row count is not a multiple of 4."""
+    n = 1001                                                     # rows = 1002, not a multiple of 4
+    sd = synth.make_state_dict(n, seed=3)
+    tab = sd["embedding.token.weight"].clone()
+    for r in range(n + 1):
+        tab[r] = tab[r % 7]
+    sd["embedding.token.weight"] = tab
+    sd["model.bias"] = torch.zeros(n + 1)
+    m = LRURec(_args(n))
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    cfg = synth.Config("ties", 64, n, 30, 64)
+    ids, _ = synth.make_sequences(cfg, seed=9)
+    for k in (20, 50):
+        res = m.retrieve(ids.cuda(), k=k, exclude_history=True, precision="fp32")
+        got_i, got_s = res["ids"].cpu().numpy(), res["scores"].cpu().numpy()
+        raw = O.last_scores(ids, sd)                                          # [B, n+1] fp32 oracle scores
+        canon = raw[:, torch.arange(n + 1) % 7]                               # one value per tied class (a CPU matmul may
+        dense = O.mask_history(canon, ids).numpy()                            # round identical rows differently); history
+        for b in range(ids.shape[0]):                                         # and item 0 at -1e9
+            order = np.lexsort((np.arange(n + 1), -dense[b]))                 # score desc, id asc
+            want = [int(i) for i in order[:k]]
+            assert got_i[b].tolist() == want, (k, b, got_i[b][:8], want[:8])
+            np.testing.assert_allclose(got_s[b], dense[b][want], rtol=1e-5, atol=1e-6)
+    # the same through two row shards (row_offset != 0 in the second) merged like ranks would merge them
+    full = m.retrieve(ids.cuda(), k=20, exclude_history=True, precision="fp32")
+    parts_s, parts_i = [], []
+    cut = 500
+    for lo, hi in ((0, cut), (cut, n + 1)):
+        m.set_row_shard(lo, hi)
+        r = m.retrieve(ids.cuda(), k=20, exclude_history=True, precision="fp32")
+        parts_s.append(r["scores"]); parts_i.append(r["ids"])
+    m.set_row_shard(0, n + 1)
+    merged = merge_lists(torch.stack(parts_s), torch.stack(parts_i), None, k_out=20, layout="list_major")
+    assert torch.equal(merged["ids"], full["ids"]) and torch.equal(merged["scores"], full["scores"])
+
+
 def test_errors_are_loud():
     from llamarec_b200._lib import LrbError
     m = LRURec(_args(50)).cuda().eval()

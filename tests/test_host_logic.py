@@ -313,3 +313,54 @@ def test_gradient_blob_unpack_is_the_inverse_of_weight_packing():
             assert torch.equal(v.real, ref.real) and not v.imag.any(), k      # Im b_out never reaches the output
         else:
             assert torch.equal(v, ref), k
+
+
+def test_radix_select_algorithm_equals_sorted_topk_with_ties():
+    """numpy transliteration of select_topk_kernel (csrc/score.cu: exact-fp32 path of small catalogues): 4 passes of
+    8 bits over the order-preserving key find the K-th largest key, everything above it plus the lowest-id entries
+    equal to it are collected, -inf / NaN entries are dropped, the survivors are rank-sorted (score desc, id asc).
+    Must equal a plain sort for random rows with massive ties, masked entries, NaNs and K > valid entries."""
+    def key(v):
+        i = v.view(np.int32).astype(np.int64)
+        k = np.where(i >= 0, i, i ^ 0x7fffffff)                      # float_to_key
+        k = (k & 0xffffffff) ^ 0x80000000
+        return np.where(np.isnan(v), 0, k).astype(np.uint64)
+
+    def select(row, K):
+        rows = len(row)
+        keys = key(row)
+        K_eff = min(K, rows)
+        prefix, need = 0, K_eff
+        for p in range(4):
+            shift = 24 - 8 * p
+            hi_mask = 0 if p == 0 else (0xffffffff << (shift + 8)) & 0xffffffff
+            act = (keys & hi_mask) == prefix
+            hist = np.bincount(((keys[act] >> shift) & 255).astype(np.int64), minlength=256)
+            acc = 0
+            for b in range(255, -1, -1):                             # highest bin first
+                if acc < need <= acc + hist[b]:
+                    prefix |= b << shift
+                    need -= acc
+                    break
+                acc += hist[b]
+        gt = np.nonzero(keys > prefix)[0]
+        eq = np.nonzero(keys == prefix)[0][:need]                    # lowest columns first
+        assert len(gt) == K_eff - need
+        cand = np.concatenate([gt, eq])
+        cand = [c for c in cand if row[c] > -np.inf]                 # NaN > -inf is False as well
+        cand.sort(key=lambda c: (-row[c], c))
+        return cand
+
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        rows = int(rng.integers(1, 700))
+        K = int(rng.choice([1, 5, 20, 50]))
+        row = rng.choice(rng.standard_normal(max(2, rows // 9)).astype(np.float32), size=rows).astype(np.float32)
+        row[rng.random(rows) < 0.2] = -np.inf                       # history mask
+        if trial % 3 == 0:
+            row[rng.random(rows) < 0.05] = np.nan
+        if trial % 7 == 0:
+            row[:] = -np.inf if trial % 2 else np.float32(0.0)       # everything masked / everything tied (+0.0)
+        valid = [c for c in range(rows) if row[c] > -np.inf]
+        want = sorted(valid, key=lambda c: (-row[c], c))[:K]
+        assert select(row, K) == want, (trial, rows, K)
