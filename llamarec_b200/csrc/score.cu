@@ -169,10 +169,10 @@ __global__ void __launch_bounds__(ROWS) score_f32_kernel(const Params p) {
   }
 }
 
-inline int splits_for(int B, long long rows, int sms) {
+inline int splits_for(int B, long long rows, int sms, int ctas_per_sm = 2) {
   const int m_tiles = (B + ROWS - 1) / ROWS;
   const long long chunks = (rows + IT - 1) / IT;
-  long long want = (2LL * sms + m_tiles - 1) / m_tiles;
+  long long want = (static_cast<long long>(ctas_per_sm) * sms + m_tiles - 1) / m_tiles;
   long long max_splits = (chunks + 3) / 4;   // at least 4 chunks (256 items) per split
   if (max_splits < 1) max_splits = 1;
   if (want > max_splits) want = max_splits;
@@ -673,7 +673,7 @@ int lrb_score_topk(const void* u, const void* table, const float* bias_pad, cons
       p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
       p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
       p.dense_out = dense; p.dense_ld = ld;
-      const int splits = f32::splits_for(nb, rows, sms);
+      const int splits = f32::splits_for(nb, rows, sms, 4);   // dense variant: 49 KB / 96 registers -> 4 CTAs per SM
       dim3 grid(static_cast<unsigned>((nb + f32::ROWS - 1) / f32::ROWS), splits);
       dkern<<<grid, f32::ROWS, smem, st>>>(p);
       LRB_CUDA_TRY(cudaGetLastError());
@@ -832,7 +832,7 @@ int lrb_score_dense(const void* x, const void* table, const float* bias_pad, con
     p.excl_sorted = nullptr; p.excl_bloom = nullptr; p.excl_stride = 0;
     p.part_scores = nullptr; p.part_ids = nullptr; p.part_cnt = nullptr; p.slots = 0;
     p.dense_out = out; p.dense_ld = ld_out;
-    const int splits = f32::splits_for(static_cast<int>(M), rows, sms);
+    const int splits = f32::splits_for(static_cast<int>(M), rows, sms, 4);
     const size_t smem = (f32::IT * f32::D + f32::IT) * 4 + static_cast<size_t>(f32::ROWS) * (f32::IT + 1) * 4;
     auto kern = f32::score_f32_kernel<true>;
     LRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
