@@ -54,3 +54,35 @@ def rerank_metrics(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int]
     """`compute_metrics_for_ks(ks, verbalizer)` (trainer/llm.py:63-72) for label scores that are already on the
     device: Recall/MRR/NDCG@ks of the label index among the C candidates, same keys as the reference."""
     return absolute_recall_mrr_ndcg_for_ks(scores, labels.view(-1), list(ks))
+
+
+# ---- the demo's retriever artefact (setup_demo.py:46-47, demo/inference.py:20-23,46-53) ------------------------------
+def export_retriever(model, path: str) -> None:
+    """What `torch.jit.script(model).save("demo/retriever.pth")` is to the reference demo (setup_demo.py:46-47): one
+    file the demo can load without the training code.  The kernels are reached through a C ABI, which TorchScript
+    cannot trace, so the artefact is the model's hyper-parameters + `state_dict` (the reference's own keys and dtypes);
+    `load_retriever` rebuilds the `LRURec` from it."""
+    args = model.args
+    keep = {k: getattr(args, k) for k in ("num_items", "bert_hidden_units", "bert_num_blocks", "bert_dropout",
+                                           "bert_attn_dropout") if hasattr(args, k)}
+    torch.save({"format": "llamarec_b200.retriever.v1", "args": keep,
+                "state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}}, path)
+
+
+def load_retriever(path: str = "retriever.pth", device: str = "cuda"):
+    """demo/inference.py:20-23 -- load the exported retriever, in eval mode, on `device`."""
+    from types import SimpleNamespace
+    from .model import LRURec
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    if blob.get("format") != "llamarec_b200.retriever.v1":
+        raise ValueError(f"{path} is not a llamarec_b200 retriever export")
+    model = LRURec(SimpleNamespace(**blob["args"]))
+    model.load_state_dict(blob["state_dict"])
+    return model.to(device).eval()
+
+
+def retrieve_candidates(model, query: Sequence[int], top_k: int = 20) -> List[int]:
+    """demo/inference.py:46-53: `topk(model(seqs)[:, -1, :], top_k)` for one interaction history, without the history
+    mask (the demo does not apply one) and without the [1, L, N+1] score tensor."""
+    seqs = torch.tensor(list(query), dtype=torch.int64).unsqueeze(0)
+    return model.retrieve(seqs, k=top_k, exclude_history=False)["ids"][0].tolist()

@@ -610,6 +610,22 @@ def test_exact_fp32_selection_with_massive_ties_and_row_shards():
     assert torch.equal(merged["ids"], full["ids"]) and torch.equal(merged["scores"], full["scores"])
 
 
+def test_demo_retriever_export_and_retrieve_candidates(tmp_path, model, golden_sd):
+    """The demo's path (setup_demo.py:46-47, demo/inference.py:20-23,46-53): export the retriever, load it back on the
+    GPU, `retrieve_candidates(model, history, top_k)` == topk of the oracle's last-position scores (no history mask)."""
+    from llamarec_b200 import stage2
+    path = str(tmp_path / "retriever.pth")
+    stage2.export_retriever(model, path)
+    loaded = stage2.load_retriever(path, device="cuda")
+    hist = [int(v) for v in load_case("left_l20")["ids"][0] if v > 0]
+    got = stage2.retrieve_candidates(loaded, hist, top_k=20)
+    x = torch.tensor(hist).unsqueeze(0)
+    res = loaded.retrieve(x.cuda(), k=20, exclude_history=False)
+    assert got == res["ids"][0].tolist()
+    ref_s, ref_i = O.retrieve(x, golden_sd, 20, exclude_history=False)
+    assert_topk_equivalent(res["ids"].cpu().numpy(), res["scores"].cpu().numpy(), ref_i.numpy(), ref_s.numpy())
+
+
 def test_errors_are_loud():
     from llamarec_b200._lib import LrbError
     m = LRURec(_args(50)).cuda().eval()

@@ -364,3 +364,26 @@ def test_radix_select_algorithm_equals_sorted_topk_with_ties():
         valid = [c for c in range(rows) if row[c] > -np.inf]
         want = sorted(valid, key=lambda c: (-row[c], c))[:K]
         assert select(row, K) == want, (trial, rows, K)
+
+
+def test_retriever_export_round_trip(tmp_path):
+    """stage2.export_retriever / load_retriever (the demo's retriever artefact, setup_demo.py:46-47,
+    demo/inference.py:20-23): every parameter of the reference's state_dict survives the file, keys and dtypes
+    included; a foreign file is rejected."""
+    from types import SimpleNamespace
+    from llamarec_b200 import LRURec, stage2, synth
+    sd = synth.make_state_dict(120, seed=4, bias_std=0.02)
+    m = LRURec(SimpleNamespace(num_items=120, bert_hidden_units=64, bert_num_blocks=2, bert_dropout=0.2,
+                               bert_attn_dropout=0.2))
+    m.load_state_dict(sd)
+    path = str(tmp_path / "retriever.pth")
+    stage2.export_retriever(m, path)
+    back = stage2.load_retriever(path, device="cpu")
+    assert not back.training and back.num_items == 120
+    got = back.state_dict()
+    assert set(got) == set(sd)
+    for k, v in sd.items():
+        assert got[k].dtype == v.dtype and torch.equal(got[k], v), k
+    torch.save({"format": "something else"}, path)
+    with pytest.raises(ValueError):
+        stage2.load_retriever(path, device="cpu")
