@@ -84,5 +84,8 @@ def load_retriever(path: str = "retriever.pth", device: str = "cuda"):
 def retrieve_candidates(model, query: Sequence[int], top_k: int = 20) -> List[int]:
     """demo/inference.py:46-53: `topk(model(seqs)[:, -1, :], top_k)` for one interaction history, without the history
     mask (the demo does not apply one) and without the [1, L, N+1] score tensor."""
-    seqs = torch.tensor(list(query), dtype=torch.int64).unsqueeze(0)
+    query = list(query)
+    if not query:
+        raise ValueError("retrieve_candidates needs at least one interaction")
+    seqs = torch.tensor(query, dtype=torch.int64).unsqueeze(0)
     return model.retrieve(seqs, k=top_k, exclude_history=False)["ids"][0].tolist()

@@ -617,7 +617,10 @@ def test_demo_retriever_export_and_retrieve_candidates(tmp_path, model, golden_s
     path = str(tmp_path / "retriever.pth")
     stage2.export_retriever(model, path)
     loaded = stage2.load_retriever(path, device="cuda")
-    hist = [int(v) for v in load_case("left_l20")["ids"][0] if v > 0]
+    rows = load_case("left_l20")["ids"]
+    hist = next([int(v) for v in r if v > 0] for r in rows if (r > 0).sum() >= 3)   # (the fixture also has empty rows)
+    with pytest.raises(ValueError):
+        stage2.retrieve_candidates(loaded, [], top_k=5)
     got = stage2.retrieve_candidates(loaded, hist, top_k=20)
     x = torch.tensor(hist).unsqueeze(0)
     res = loaded.retrieve(x.cuda(), k=20, exclude_history=False)
