@@ -45,9 +45,10 @@ constexpr int HN = 128;                     // accumulator columns per half-tile
 constexpr int ACC_STAGES = 4;
 constexpr int TMEM_COLS = ACC_STAGES * HN;
 constexpr int DONE_RING = 8;                // tiles in the ring of "half-tile computed" barriers (two per tile); must exceed the TMA ring depth
-// Epilogue warps of the K <= 20 kernel: 8 (two 128-column parts per tile) or 16 (four 64-column parts).  Measured on
-// B200 (10M rows, 4096 users): 16 warps read the accumulators a little faster in isolation (tools/epi_probe: 702 vs 757
-// cycles per tile) but lose in the kernel (96 registers per thread, twice the per-thread candidate sets): 5.86 vs 5.25 ms.
+// Epilogue warps: 8 (two column parts).  A 16-warp variant (four 64-column parts) was measured on B200 with the
+// two-stage kernel of early round 2 (10M rows, 4096 users): it read the accumulators a little faster in isolation
+// (tools/epi_probe: 702 vs 757 cycles per tile) but lost in the kernel (96 registers per thread, twice the per-thread
+// candidate sets): 5.86 vs 5.25 ms; the kernel below is written for 8.
 #ifndef LRB_EW20
 #define LRB_EW20 8
 #endif
